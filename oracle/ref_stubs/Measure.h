@@ -1,0 +1,4 @@
+/* empty stand-in for a VMD header that is not in the reference snapshot (oracle/_ref build only) */
+#ifndef STUB_Measure_H
+#define STUB_Measure_H
+#endif
