@@ -1,0 +1,195 @@
+/*
+ * voltool_gpu.h -- C ABI of libvoltool_gpu.so, the B200 (sm_100a) drop-in for voltool's
+ * data-parallel hot path.  Plain pointers and sizes only; no C++/torch types cross this line.
+ *
+ * Every entry point names the reference interface it replaces (file:line into the
+ * ryanmcgreevy/voltool snapshot).  INTEGRATION.md shows the replacement bodies a VMD maintainer
+ * would put into MDFF.C / VolumetricData.C / Voltool.C / TclVoltool.C to call these.
+ *
+ * Conventions
+ *   - every function returns 0 on success, nonzero on failure; vt_last_error() holds the text.
+ *     There is no CPU fallback: without a usable CUDA device vt_init() fails and so does
+ *     everything else.
+ *   - vt_map is the resident twin of VolumetricData (VolumetricData.h:27-36): a float grid in
+ *     HBM (x fastest, then y, then z) + double origin/axes + the cached min/max/mean/sigma block
+ *     (VolumetricData.h:202-210) maintained by exactly the reference's invalidation rules.
+ *   - "host" variants take host pointers, copy in, run, copy out (one call = one reference call).
+ *   - single Tcl thread model (tcl_commands.C:291-295): the library keeps one process-global
+ *     context and is not re-entrant.
+ */
+#ifndef VOLTOOL_GPU_H
+#define VOLTOOL_GPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* mirrors VolumetricData.h:29-33 */
+typedef struct vt_grid {
+  double origin[3];
+  double xaxis[3];
+  double yaxis[3];
+  double zaxis[3];
+  int xsize, ysize, zsize;
+} vt_grid;
+
+/* mirrors the cached-statistics block, VolumetricData.h:202-210 */
+typedef struct vt_cache {
+  int minmax_valid, mean_valid, sigma_valid;
+  float cmin, cmax, cmean, csigma;
+} vt_cache;
+
+typedef struct vt_map vt_map; /* opaque resident map */
+
+/* ---------------------------------------------------------------- lifecycle */
+/* device < 0: honour VOLTOOL_GPU_DEVICE, else LOCAL_RANK, else 0.  Replaces the
+   "vmdinfo numcudadevices"/VMDCUDA bring-up the old hooks relied on (tcl_commands.C:107-118). */
+int vt_init(int device);
+int vt_shutdown(void);
+int vt_sync(void);
+const char *vt_last_error(void);
+/* sm_count, max SM clock (kHz), total device memory; any pointer may be NULL */
+int vt_device_props(int *sm_count, int *clock_khz, size_t *mem_bytes, char *name, int name_len);
+/* number of kernels this library has launched since vt_init (bench.py's gpu_launches) */
+long vt_launch_count(void);
+/* all library work runs on one stream; torch callers use this to order their own events */
+void *vt_stream(void);
+
+/* ---------------------------------------------------------------- resident maps */
+/* VolumetricData::VolumetricData (VolumetricData.C:66-89): adopts a copy of host_data and runs
+   compute_minmax() like the constructor does.  host_data == NULL gives a zero-filled map. */
+int vt_map_create(const vt_grid *g, const float *host_data, vt_map **out);
+/* as above from a DEVICE pointer (device-to-device copy) */
+int vt_map_create_from_device(const vt_grid *g, const float *dev_data, vt_map **out);
+int vt_map_clone(const vt_map *m, vt_map **out);
+int vt_map_destroy(vt_map *m); /* VolumetricData::~VolumetricData, VolumetricData.C:93-99 */
+int vt_map_grid(const vt_map *m, vt_grid *g);
+int vt_map_cache(const vt_map *m, vt_cache *c);
+long vt_map_gridsize(const vt_map *m); /* VolumetricData::gridsize, VolumetricData.h:78-80 */
+int vt_map_download(const vt_map *m, float *host_out);
+int vt_map_upload(vt_map *m, const float *host_in); /* replaces data, reruns compute_minmax */
+float *vt_map_device_ptr(vt_map *m);
+
+/* ---------------------------------------------------------------- cross correlation */
+/* cc_threaded(qsVol, targetVol, &cc, threshold)  MDFF.C:102-151 (+ correlationthread :55-99).
+   A is the thresholded map (MDFF.C:77).  nused/sums may be NULL; sums = {sumA, sumB, sumAA,
+   sumBB, sumAB}. */
+int vt_cc(const vt_map *A, const vt_map *B, double threshold, double *cc, long *nused, double sums[5]);
+int vt_cc_host(const vt_grid *gA, const float *a, const vt_grid *gB, const float *b, double threshold,
+               double *cc);
+
+/* ---------------------------------------------------------------- unary streams (in place) */
+int vt_clamp(vt_map *m, float min_value, float max_value);            /* VolumetricData::clamp :634-653 */
+int vt_scale_by(vt_map *m, float ff);                                 /* ::scale_by :656-677 */
+int vt_scalar_add(vt_map *m, float ff);                               /* ::scalar_add :680-694 */
+int vt_rescale_voxel_value_range(vt_map *m, float min_value, float max_value); /* :697-714 */
+int vt_sigma_scale(vt_map *m);                                        /* ::sigma_scale :937-953 */
+int vt_binmask(vt_map *m, float threshold);                           /* ::binmask :957-969 */
+int vt_mdff_potential(vt_map *m, double threshold);                   /* ::mdff_potential :999-1025 */
+
+/* ---------------------------------------------------------------- statistics */
+int vt_datarange(vt_map *m, float *min_value, float *max_value);      /* ::datarange :1035-1044 */
+int vt_mean(vt_map *m, float *mean);                                  /* ::mean :1078-1086 */
+int vt_sigma(vt_map *m, float *sigma);                                /* ::sigma :1095-1100 */
+int vt_vol_com(const vt_map *m, float com[3]);                        /* vol_com, Voltool.C:229-247 */
+int vt_histogram(vt_map *m, int nbins, long *bins, float *midpts);    /* histogram, Voltool.C:443-461 */
+
+/* ---------------------------------------------------------------- resizing ops (replace data) */
+int vt_pad(vt_map *m, int padxm, int padxp, int padym, int padyp, int padzm, int padzp); /* ::pad :542-609; trim = pad(-t) TclVoltool.C:1185 */
+int vt_crop(vt_map *m, double minx, double miny, double minz, double maxx, double maxy, double maxz); /* ::crop :615-631 */
+int vt_downsample(vt_map *m);                                         /* ::downsample :720-769 */
+int vt_supersample(vt_map *m);                                        /* ::supersample :773-932 */
+int vt_gaussian_blur(vt_map *m, double sigma);                        /* ::gaussian_blur :977-997 */
+
+/* ---------------------------------------------------------------- two-map ops */
+enum { VT_ADD = 0, VT_SUBTRACT = 1, VT_MULTIPLY = 2, VT_AVERAGE = 3 };
+/* add/subtract/multiply/average(mapA, mapB, newvol, interp, USE_UNION)  Voltool.C:249-377,
+   output grid from init_from_union / init_from_intersection (Voltool.C:51-147) */
+int vt_binary(int op, int interp, int use_union, const vt_map *A, const vt_map *B, vt_map **out);
+int vt_binary_host(int op, int interp, int use_union, const vt_grid *gA, const float *a, const vt_grid *gB,
+                   const float *b, vt_grid *out_grid, float **out_data /* malloc()ed; vt_free_host */);
+void vt_free_host(void *p);
+/* geometry only (host double arithmetic, identical to the reference expressions) */
+int vt_init_from_intersection(const vt_grid *A, const vt_grid *B, vt_grid *out); /* Voltool.C:51-78 */
+int vt_init_from_union(const vt_grid *A, const vt_grid *B, vt_grid *out);        /* Voltool.C:114-147 */
+
+/* ---------------------------------------------------------------- sim (density map from atoms) */
+/* parameter policy of mdff_sim / mdff_cc / calc_cc: TclMDFF.C:125-135, 397-401, 492-494 */
+int vt_sim_policy(double resolution, double gspacing_in, float *radscale, double *gspacing, int *quality);
+/* QuickSurf::calc_density_map(sel, mol, pos, radii, quality, radscale, gspacing)
+   call sites TclMDFF.C:154-157, 496-499; TclVoltool.C:119-122.  pos = 3*natoms, radii = natoms
+   (selected atoms only, compacted by the caller exactly as the Tcl wrappers' AtomSel loop does). */
+int vt_sim(const float *pos, const float *radii, long natoms, int quality, float radscale, float gspacing,
+           vt_map **out);
+/* calc_cc(sel, target, resolution, ...)  TclVoltool.C:73-129: policy + sim + cc(threshold 0.1) */
+int vt_calc_cc(const float *pos, const float *radii, long natoms, const vt_map *target, float resolution,
+               double *cc);
+/* mdff_cc's CPU branch TclMDFF.C:486-524: sim at the given policy then cc_threaded(sim, target) */
+int vt_sim_cc(const float *pos, const float *radii, long natoms, double resolution, double gspacing_in,
+              const vt_map *target, double threshold, double *cc, vt_map **synth_out /* may be NULL */);
+
+/* ---------------------------------------------------------------- fit (rigid-body pose search) */
+/* one candidate of rotate() (TclVoltool.C:160-176) or of an explicit pose list: rotate about
+   com by Euler angles (degrees, X then Y then Z, each a separate rounded pass like do_rotate
+   :131-136), translate back by +com, then by shift (extension; {0,0,0} for the reference). */
+typedef struct vt_pose {
+  float rot_deg[3];
+  float shift[3];
+} vt_pose;
+
+typedef struct vt_fit_result {
+  float best_cc;      /* "Best CC" TclVoltool.C:926 */
+  float com[3];       /* structure centre after the COM alignment, :803 */
+  float dencom[3];    /* vol_com(target), :799 */
+  int n_evaluated;    /* candidates the reference's sequential loop visits (skip rule :186-190) */
+  int n_computed;     /* candidates this library actually evaluated (all of them) */
+  int stage_best[5];  /* winning index per rotate() call, -1 if that call found nothing better */
+  float exhaustive_cc;   /* argmax over every evaluated candidate of the final stage set */
+} vt_fit_result;
+
+typedef struct vt_fit_ctx vt_fit_ctx;
+
+/* resident state for a pose search: target map, atoms (origin coordinates), radii.  The target
+   is borrowed (must outlive the ctx). */
+int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_map *target, float resolution,
+                  vt_fit_ctx **out);
+int vt_fit_destroy(vt_fit_ctx *ctx);
+int vt_fit_set_origin(vt_fit_ctx *ctx, const float *pos); /* reset_origin, TclVoltool.C:314-318 */
+/* evaluate poses [0,nposes) of a list; cc_out[i] = (float)calc_cc for pose i (host buffers) */
+int vt_fit_eval_poses(vt_fit_ctx *ctx, const float com[3], const vt_pose *poses, long nposes, float *cc_out);
+/* same with the pose list already uploaded and the result left on the device (for benchmarks and
+   for NCCL allgather directly from device memory); d_poses/d_cc are device pointers */
+int vt_fit_eval_poses_device(vt_fit_ctx *ctx, const float com[3], const vt_pose *d_poses, long nposes,
+                             float *d_cc);
+/* all max_rot^3 candidates of one rotate() call; table[x*m*m+y*m+z]; only entries
+   first, first+step, ... are written (sharding across ranks) */
+int vt_fit_rotate_table(vt_fit_ctx *ctx, const float com[3], int stride, int max_rot, int first, int step,
+                        float *table);
+/* the reference's sequential loop incl. the skip rule, driven from a table (TclVoltool.C:160-199) */
+int vt_rotate_replay(const float *table, int max_rot, float *returncc, int *best_idx);
+/* apply one candidate transform to host coordinates with the reference's rounding (do_rotate etc.) */
+int vt_pose_apply(float *pos, long natoms, const float com[3], const vt_pose *pose);
+int vt_measure_center(const float *pos, const float *weight, long natoms, float com[3]); /* TclVoltool.C:789 */
+
+/* multi-GPU: the pose search is the only sharded path.  rank r evaluates candidates r, r+world, ...
+   and the per-stage tables are merged by the caller-supplied allgather (torch.distributed/NCCL in
+   voltool_b200.dist).  merge(table, n, rank, world, user) must leave the complete table on every rank. */
+typedef int (*vt_table_merge_fn)(float *table, int n, int rank, int world, void *user);
+int vt_fit_set_shard(int rank, int world, vt_table_merge_fn merge, void *user);
+/* evaluator hook: by default the CUDA pose evaluator; host-logic tests inject their own */
+typedef int (*vt_table_eval_fn)(void *user, const float *origin_pos, const float com[3], int stride, int max_rot,
+                                int first, int step, float *table);
+/* fit(): TclVoltool.C:784-916.  pos updated in place with the best pose's coordinates. */
+int vt_fit(float *pos, const float *radii, const float *mass, long natoms, const vt_map *target, float resolution,
+           vt_fit_result *res);
+/* the schedule alone (COM alignment, 3-stage Euler schedule, replay, commit) with an injected
+   evaluator; dencom is vol_com(target) supplied by the caller.  No CUDA is touched. */
+int vt_fit_schedule(float *pos, const float *mass, long natoms, const float dencom[3], vt_table_eval_fn eval,
+                    void *user, vt_fit_result *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -52,50 +52,38 @@ void vo_mat4_identity(float m[16]) {
   m[0] = m[5] = m[10] = m[15] = 1.0f;
 }
 
-/* In-place Gauss-Jordan elimination with full pivoting, all arithmetic in float.
-   Returns 1 if singular (matrix left partially reduced, as a failed inverse would be). */
+/* Gauss-Jordan on the augmented [M | I], all arithmetic in float, eliminating on the DIAGONAL
+   pivots in order; rows are exchanged only when a diagonal pivot is exactly zero (then with the
+   row below holding the largest entry of that column).  For the cell matrices voltool builds
+   (diagonal 3x3 + translation row, VolumetricData.C:207-223) no exchange happens and every
+   structural zero of the inverse stays an exact zero.  Returns 1 if singular. */
 int vo_mat4_inverse(float m[16]) {
-  float a[4][4];
-  int done[4] = {0, 0, 0, 0};
-  int prow[4], pcol[4];
-  for (int i = 0; i < 4; i++)
-    for (int j = 0; j < 4; j++) a[i][j] = m[4 * i + j];
-
-  for (int step = 0; step < 4; step++) {
-    float big = 0.0f;
-    int r = 0, c = 0;
-    for (int i = 0; i < 4; i++) {
-      if (done[i] == 1) continue;
-      for (int j = 0; j < 4; j++) {
-        if (done[j] != 0) continue;
-        float v = fabsf(a[i][j]);
-        if (v >= big) { big = v; r = i; c = j; }
-      }
+  float w[4][8];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      w[r][c] = m[4 * r + c];
+      w[r][4 + c] = (r == c) ? 1.0f : 0.0f;
     }
-    done[c] += 1;
-    if (r != c) {
-      for (int l = 0; l < 4; l++) { float t = a[r][l]; a[r][l] = a[c][l]; a[c][l] = t; }
+  for (int i = 0; i < 4; i++) {
+    if (w[i][i] == 0.0f) {
+      int p = -1;
+      float big = 0.0f;
+      for (int j = i + 1; j < 4; j++)
+        if (fabsf(w[j][i]) > big) { big = fabsf(w[j][i]); p = j; }
+      if (p < 0) return 1;
+      for (int c = 0; c < 8; c++) { float t = w[i][c]; w[i][c] = w[p][c]; w[p][c] = t; }
     }
-    prow[step] = r;
-    pcol[step] = c;
-    if (a[c][c] == 0.0f) return 1;
-    float pinv = 1.0f / a[c][c];
-    a[c][c] = 1.0f;
-    for (int l = 0; l < 4; l++) a[c][l] *= pinv;
-    for (int i = 0; i < 4; i++) {
-      if (i == c) continue;
-      float f = a[i][c];
-      a[i][c] = 0.0f;
-      for (int l = 0; l < 4; l++) a[i][l] -= a[c][l] * f;
+    float s = 1.0f / w[i][i];
+    for (int c = 0; c < 8; c++) w[i][c] *= s;
+    for (int r = 0; r < 4; r++) {
+      if (r == i) continue;
+      float f = w[r][i];
+      if (f == 0.0f) continue;
+      for (int c = 0; c < 8; c++) w[r][c] -= w[i][c] * f;
     }
   }
-  for (int l = 3; l >= 0; l--) {
-    if (prow[l] != pcol[l]) {
-      for (int k = 0; k < 4; k++) { float t = a[k][prow[l]]; a[k][prow[l]] = a[k][pcol[l]]; a[k][pcol[l]] = t; }
-    }
-  }
-  for (int i = 0; i < 4; i++)
-    for (int j = 0; j < 4; j++) m[4 * i + j] = a[i][j];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) m[4 * r + c] = w[r][4 + c];
   return 0;
 }
 

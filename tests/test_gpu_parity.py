@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Bit-exact for elementwise ops, indexing, resampling; 1e-5 relative for sim voxels and CC
+(north_star tolerance); CC of map pairs to 1e-9 (only the double summation order differs)."""
+import numpy as np
+import pytest
+
+import voltool_b200 as vt
+from oracle.pyoracle import Grid as OGrid
+from tests.synth import make_structure, make_target
+
+pytestmark = pytest.mark.gpu
+FLT_MAX = 3.4028234663852886e38
+
+
+def G(g):
+    return vt.Grid.from_fields(g)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def rng_map(seed, n):
+    return np.random.default_rng(seed).random(n, dtype=np.float32)
+
+
+def grids():
+    return [OGrid.make((0.0, 0.0, 0.0), (20, 18, 16), 1.0),
+            OGrid.make((0.5, -1.25, 2.0), (17, 21, 13), (1.1, 0.9, 1.3)),
+            OGrid.make((-3.3, 1.7, 0.4), (25, 12, 19), 0.77),
+            OGrid.make((1.0e-3, 5.5, -2.0), (9, 31, 14), (2.0, 0.5, 1.0))]
+
+
+def skewed_grid():
+    # non-orthogonal cell: forces the generic (per-voxel matrix) path
+    return OGrid.make((0.3, 0.1, -0.2), (15, 14, 13), axes=((14.0, 1.0, 0.0), (0.5, 13.0, 0.7), (0.0, 0.3, 12.0)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    vt.init(0)
+    yield
+
+
+# ------------------------------------------------------------------------------------------ cc
+@pytest.mark.parametrize("thr", [-FLT_MAX, 0.3])
+def test_cc_pairs(oracle, thr):
+    gs = grids()
+    for i, A in enumerate(gs):
+        for j, B in enumerate(gs):
+            a, b = rng_map(10 + i, A.n), rng_map(20 + j, B.n)
+            if oracle.intersection(A, B).n <= 0:
+                continue
+            want, nw, sw = oracle.cc(A, a, B, b, thr, full=True)
+            got, ng, sg = vt.cc_threaded(vt.VolMap(G(A), a), vt.VolMap(G(B), b), thr, full=True)
+            assert ng == nw
+            if np.isnan(want):
+                assert np.isnan(got)
+            else:
+                assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (i, j, got, want)
+                assert np.allclose(sg, sw, rtol=1e-6, atol=1e-6)
+
+
+def test_cc_generic_path_matches(oracle, monkeypatch):
+    A, B = grids()[0], grids()[1]
+    a, b = rng_map(1, A.n), rng_map(2, B.n)
+    want = oracle.cc(A, a, B, b, 0.2)
+    monkeypatch.setenv("VOLTOOL_FORCE_GENERIC", "1")
+    got = vt.cc_threaded(vt.VolMap(G(A), a), vt.VolMap(G(B), b), 0.2)
+    assert abs(got - want) <= 1e-12
+    # skewed cells take the generic path on their own
+    monkeypatch.delenv("VOLTOOL_FORCE_GENERIC")
+    S = skewed_grid()
+    s = rng_map(3, S.n)
+    want = oracle.cc(S, s, A, a, -FLT_MAX)
+    got = vt.cc_threaded(vt.VolMap(G(S), s), vt.VolMap(G(A), a), -FLT_MAX)
+    assert abs(got - want) <= 1e-9
+
+
+def test_cc_known_answers():
+    g = vt.Grid.make((0, 0, 0), (64, 60, 56), 1.0)
+    a = rng_map(5, g.n)
+    u = rng_map(6, g.n)
+    A = vt.VolMap(g, a)
+    assert abs(vt.cc_threaded(A, A) - 1.0) < 1e-9
+    assert abs(vt.cc_threaded(A, vt.VolMap(g, -a)) + 1.0) < 1e-9
+    b = (0.7 * a + 0.3 * u).astype(np.float32)
+    assert abs(vt.cc_threaded(A, vt.VolMap(g, b)) - 0.7 / np.sqrt(0.58)) < 5e-3
+    # invariance to a positive affine rescale of either map
+    c1 = vt.cc_threaded(A, vt.VolMap(g, b))
+    c2 = vt.cc_threaded(A, vt.VolMap(g, (3.0 * b + 1.0).astype(np.float32)))
+    assert abs(c1 - c2) < 1e-5
+
+
+def test_cc_nan_and_threshold(oracle):
+    A, B = grids()[0], grids()[2]
+    a, b = rng_map(7, A.n), rng_map(8, B.n)
+    a[::17] = np.nan
+    b[::29] = np.nan
+    for thr in (-FLT_MAX, 0.5):
+        want, nw, _ = oracle.cc(A, a, B, b, thr, full=True)
+        got, ng, _ = vt.cc_threaded(vt.VolMap(G(A), a), vt.VolMap(G(B), b), thr, full=True)
+        assert ng == nw and abs(got - want) <= 1e-9
+
+
+# ------------------------------------------------------------------------------------------ two-map ops
+@pytest.mark.parametrize("op", [0, 1, 2, 3])
+@pytest.mark.parametrize("interp", [True, False])
+@pytest.mark.parametrize("use_union", [True, False])
+def test_binary_ops_bit_exact(oracle, op, interp, use_union):
+    gs = grids()[:3] + [skewed_grid()]
+    for i, A in enumerate(gs):
+        for j, B in enumerate(gs):
+            if use_union and (i == 3 or j == 3):
+                continue  # init_from_union is orthogonal-only (Voltool.C:118-133)
+            a, b = rng_map(30 + i, A.n) - 0.25, rng_map(40 + j, B.n) - 0.25
+            og, want = oracle.binary(op, A, a, B, b, interp, use_union)
+            if og.n <= 0:
+                continue
+            got = vt.binary(op, vt.VolMap(G(A), a), vt.VolMap(G(B), b), interp, use_union)
+            assert got.grid.astuple() == og.astuple()
+            assert np.array_equal(bits(got.data), bits(want)), (op, interp, use_union, i, j)
+
+
+# ------------------------------------------------------------------------------------------ unary + stats
+def test_unary_sequence_bit_exact(oracle):
+    g = OGrid.make((1.0, 2.0, 3.0), (22, 17, 19), 1.25)
+    d0 = (rng_map(5, g.n) * 4 - 1).astype(np.float32)
+    seq = [("clamp", (-0.5, 2.5)), ("scale_by", (-1.5,)), ("scalar_add", (0.75,)), ("rescale_range", (0.0, 1.0)),
+           ("sigma_scale", ()), ("mdff_potential", (0.2,)), ("scale_by", (3.0,)), ("binmask", (1.0,))]
+    names = {"rescale_range": "rescale_voxel_value_range"}
+    m = vt.VolMap(G(g), d0)
+    d = d0.copy()
+    c = oracle.new_cache(g, d)
+    assert c.astuple() == m.cache.astuple()
+    for name, params in seq:
+        getattr(m, names.get(name, name))(*params)
+        d = oracle.unary(name, g, d, c, *params)
+        assert np.array_equal(bits(m.data), bits(d)), name
+        assert c.astuple() == m.cache.astuple(), name
+    assert oracle.sigma(g, d, c) == m.sigma()
+    assert oracle.mean(g, d, c) == m.mean()
+    assert oracle.datarange(g, d, c) == m.datarange()
+    assert c.astuple() == m.cache.astuple()
+
+
+def test_stats(oracle):
+    for k, g in enumerate(grids()):
+        d = rng_map(60 + k, g.n) * 3 - 1
+        m = vt.VolMap(G(g), d)
+        c = oracle.new_cache(g, d)
+        # double sums in a different order: identical after the float cast except on a rounding tie
+        assert abs(m.mean() - oracle.mean(g, d, c)) <= 1.2e-7 * abs(oracle.mean(g, d, c))
+        assert abs(m.sigma() - oracle.sigma(g, d, c)) <= 1.2e-7 * abs(oracle.sigma(g, d, c))
+        assert m.datarange() == oracle.datarange(g, d, c)
+        b1, m1 = oracle.histogram(g, d, c, 10)
+        b2, m2 = m.histogram(10)
+        assert np.array_equal(b1, b2) and np.array_equal(bits(m1), bits(m2))
+
+
+def test_vol_com_bit_exact(oracle):
+    for k, g in enumerate(grids()):
+        d = rng_map(70 + k, g.n) * 3 - 0.5
+        assert np.array_equal(bits(vt.VolMap(G(g), d).vol_com()), bits(oracle.vol_com(g, d)))
+
+
+def test_unaligned_sizes_and_tiny_maps(oracle):
+    for size in [(1, 1, 1), (3, 1, 2), (5, 7, 3), (33, 2, 1)]:
+        g = OGrid.make((0, 0, 0), size, 1.0)
+        d = rng_map(9, g.n) - 0.5
+        m = vt.VolMap(G(g), d)
+        c = oracle.new_cache(g, d)
+        assert m.datarange() == oracle.datarange(g, d, c)
+        m.scale_by(2.5).scalar_add(-1.0).binmask(0.1)
+        e = oracle.unary("scale_by", g, d, c, 2.5)
+        e = oracle.unary("scalar_add", g, e, c, -1.0)
+        e = oracle.unary("binmask", g, e, c, 0.1)
+        assert np.array_equal(bits(m.data), bits(e))
+
+
+# ------------------------------------------------------------------------------------------ resizing
+@pytest.mark.parametrize("pads", [(2, 3, 0, 1, 4, 0), (-2, -3, -1, 0, 0, -4), (3, -2, -1, 5, 0, 0), (-30, 0, 0, 0, 0, 0)])
+def test_pad_bit_exact(oracle, pads):
+    g = OGrid.make((1.0, -2.0, 0.5), (14, 11, 12), (1.0, 1.5, 0.8))
+    d = rng_map(3, g.n)
+    g2, want = oracle.pad(g, d, pads)
+    m = vt.VolMap(G(g), d).pad(*pads)
+    assert m.grid.astuple() == g2.astuple()
+    assert np.array_equal(bits(m.data), bits(want))
+    assert m.cache.astuple()[:3] == (0, 0, 0)
+
+
+def test_crop_bit_exact(oracle):
+    g = OGrid.make((1.0, -2.0, 0.5), (14, 11, 12), (1.0, 1.5, 0.8))
+    d = rng_map(4, g.n)
+    for box in [(3.2, 0.1, 1.9, 9.7, 8.4, 7.7), (-3.0, -5.0, -1.0, 20.0, 20.0, 12.0), (2.0, 1.0, 1.3, 30.0, 5.0, 4.1)]:
+        g2, want = oracle.crop(g, d, box)
+        m = vt.VolMap(G(g), d).crop(*box)
+        assert m.grid.astuple() == g2.astuple()
+        assert np.array_equal(bits(m.data), bits(want))
+
+
+@pytest.mark.parametrize("size", [(16, 12, 10), (15, 13, 11), (3, 4, 5), (7, 3, 9), (40, 33, 21)])
+def test_down_super_sample_bit_exact(oracle, size):
+    g = OGrid.make((0.5, 1.0, -1.0), size, 1.2)
+    d = rng_map(8, g.n) * 2 - 0.5
+    g2, want = oracle.supersample(g, d)
+    m = vt.VolMap(G(g), d).supersample()
+    assert m.grid.astuple() == g2.astuple()
+    assert np.array_equal(bits(m.data), bits(want))
+    g3, want3 = oracle.downsample(g, d)
+    m3 = vt.VolMap(G(g), d).downsample()
+    assert m3.grid.astuple() == g3.astuple()
+    assert np.array_equal(bits(m3.data), bits(want3))
+
+
+def test_supersample_known_answers():
+    # (-y0 + 5 y1 + 5 y2 - y3)/8 interior stencil; replicated ends give 3/8 on the ramp 0,1,2
+    g = vt.Grid.make((0, 0, 0), (6, 3, 3), 1.0)
+    ramp = np.tile(np.arange(6, dtype=np.float32), 9)
+    out = vt.VolMap(g, ramp).supersample().data.reshape(5, 5, 11)
+    assert out[0, 0, 3] == 1.5 and out[0, 0, 5] == 2.5
+    assert out[0, 0, 1] == 0.375
+    const = vt.VolMap(g, np.full(g.n, 2.5, np.float32)).downsample().data
+    assert np.all(const == 2.5)
+
+
+@pytest.mark.parametrize("sigma", [0.6, 1.5, 2.0])
+def test_blur_bit_exact(oracle, sigma):
+    for size in [(20, 17, 15), (64, 9, 33), (5, 4, 3)]:
+        g = OGrid.make((0, 0, 0), size, 1.0)
+        d = rng_map(9, g.n)
+        m = vt.VolMap(G(g), d).gaussian_blur(sigma)
+        assert np.array_equal(bits(m.data), bits(oracle.blur(g, d, sigma)))
+        assert m.cache.astuple()[:3] == (0, 0, 0)
+
+
+# ------------------------------------------------------------------------------------------ sim
+def rel_err(got, want):
+    return np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+
+
+@pytest.mark.parametrize("res,spacing,natoms", [(5.0, 1.0, 1500), (5.0, 0.0, 2000), (3.0, 0.0, 800), (10.0, 0.0, 600)])
+def test_sim_matches_oracle(oracle, res, spacing, natoms):
+    pos, radii, _ = make_structure(natoms, 14.0, seed=int(res * 10) + natoms)
+    radscale, gsp, quality = oracle.sim_policy(res, spacing)
+    g, want = oracle.sim(pos, radii, quality, radscale, gsp, nthreads=4)
+    m = vt.sim(pos, radii, quality, radscale, gsp)
+    assert m.grid.astuple() == g.astuple()
+    got = m.data
+    # identical support (the cutoff decisions are reproduced exactly) ...
+    assert np.array_equal(got == 0, want == 0)
+    # ... and 1e-5 relative on every voxel
+    assert rel_err(got, want).max() < 1e-5
+    mn, mx = m.datarange()
+    assert mn == got.min() and mx == got.max()
+
+
+def test_sim_single_atom_is_sampled_gaussian():
+    pos = np.array([[10.0, 11.0, 12.0]], np.float32)
+    radii = np.array([1.5], np.float32)
+    m = vt.sim(pos, radii, 3, 1.0, 0.5)
+    g = m.grid
+    d = m.data.reshape(g.zsize, g.ysize, g.xsize)
+    z, y, x = np.unravel_index(np.argmax(d), d.shape)
+    sig = 1.5
+    for dx in (0, 1, 3):
+        r2 = sum((g.origin[k] + idx * 0.5 - pos[0, k]) ** 2 for k, idx in enumerate((x + dx, y, z)))
+        assert abs(d[z, y, x + dx] - np.exp(-r2 / (2 * sig * sig))) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ calc_cc / fit
+def test_calc_cc_and_pose_batch(oracle):
+    pos, radii, mass = make_structure(1200, 13.0, seed=21)
+    g, t = make_target(oracle, pos, radii, 5.0, 1.0, rot=(24, 48, 0), noise=0.02, seed=22, mass=mass)
+    target = vt.VolMap(G(g), t)
+    want = np.float32(oracle.calc_cc(pos, radii, g, t, 5.0))
+    got = vt.calc_cc(pos, radii, target, 5.0)
+    assert abs(got - want) <= 1e-5 * abs(want)
+    com = oracle.measure_center(pos, mass)
+    assert np.array_equal(bits(vt.measure_center(pos, mass)), bits(com))
+    ctx = vt.FitContext(pos, radii, target, 5.0)
+    rots = np.array([[0, 0, 0], [24, 48, 0], [48, 24, 312], [336, 0, 24], [120, 240, 96]], np.float32)
+    cc = ctx.eval_poses(com, vt.FitContext.make_poses(rots))
+    for r, c in zip(rots, cc):
+        p = oracle.pose_transform(pos, com, 24, int(r[0]) // 24, int(r[1]) // 24, int(r[2]) // 24)
+        assert np.array_equal(bits(vt.pose_apply(pos, com, r)), bits(p))
+        w = np.float32(oracle.calc_cc(p, radii, g, t, 5.0))
+        assert abs(float(c) - float(w)) <= 1e-5 * abs(float(w)), (r, c, w)
+    # the planted pose scores best
+    assert np.argmax(cc) == 1
+    # batched == one-at-a-time (the batch path and the single path share no host code)
+    p = vt.pose_apply(pos, com, rots[2])
+    assert abs(vt.calc_cc(p, radii, target, 5.0) - float(cc[2])) <= 2e-6
+
+
+def test_rotate_table_matches_oracle_stage(oracle):
+    pos, radii, mass = make_structure(500, 10.0, seed=31)
+    g, t = make_target(oracle, pos, radii, 5.0, 1.0, rot=(4, 8, 20), noise=0.02, seed=32, mass=mass)
+    com = oracle.measure_center(pos, mass)
+    want = oracle.rotate_table(pos, radii, com, 4, 6, g, t, 5.0, nthreads=8)
+    ctx = vt.FitContext(pos, radii, vt.VolMap(G(g), t), 5.0)
+    got = ctx.rotate_table(com, 4, 6)
+    assert np.max(np.abs(got - want) / np.abs(want)) < 1e-5
+    cw, bw, vw = oracle.rotate_replay(want, 6, -1.0)
+    cg, bg, vg = vt.rotate_replay(got, 6, -1.0)
+    assert bw == bg and vw == vg and abs(cw - cg) < 1e-5
+
+
+def test_fit_matches_oracle(oracle):
+    pos, radii, mass = make_structure(400, 9.0, seed=41)
+    g, t = make_target(oracle, pos, radii, 6.0, 1.2, rot=(48, 24, 312), noise=0.01, seed=42, mass=mass, pad=6)
+    # displace the structure so the COM alignment has something to do
+    start = pos + np.array([3.0, -2.0, 1.5], np.float32)
+    p_want, r_want = oracle.fit(start, radii, mass, g, t, 6.0, direct=False, nthreads=8)
+    p_got, r_got = vt.fit(start, radii, mass, vt.VolMap(G(g), t), 6.0)
+    assert list(r_got.stage_best) == list(r_want.stage_best)
+    assert r_got.n_evaluated == r_want.n_evaluated
+    assert abs(r_got.best_cc - r_want.best_cc) <= 1e-5 * abs(r_want.best_cc)
+    assert np.array_equal(bits(np.array(r_got.dencom)), bits(np.array(r_want.dencom)))
+    assert np.array_equal(bits(p_got), bits(p_want.reshape(-1, 3)))

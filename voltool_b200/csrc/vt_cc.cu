@@ -1,0 +1,277 @@
+// vt_cc.cu -- thresholded cross correlation (cc_threaded, MDFF.C:55-151) and the two-map ops
+// add/subtract/multiply/average (Voltool.C:249-377).
+//
+// Both walk an output grid (intersection or union of the two inputs), turn each voxel index into a
+// cartesian point, and sample both source maps there.  Two code paths, selected on the host:
+//
+//   generic   any cell: the literal per-voxel arithmetic (voxel_coord -> Matrix4 product ->
+//             truncation -> 8-neighbour trilinear / nearest).
+//   separable orthogonal axis-aligned cells (the only case the reference supports, Voltool.C:55-56)
+//             where every off-diagonal term of the chain is an exact zero: voxel coordinate,
+//             truncated index, clamped neighbours and fraction depend on one axis index each, so
+//             they are tabulated per axis once (same float operations, same order => same bits)
+//             and the inner loop is table-driven.  Threads run along x and march in z, reusing
+//             the bilinear value of the shared plane between consecutive z steps when the index
+//             advances by one.
+#include <cmath>
+#include <vector>
+
+#include "vt_device.cuh"
+#include "vt_geom.h"
+#include "vt_sep.cuh"
+
+namespace vt {
+
+constexpr int kThreads = 256;
+
+static void to_dev(const vt_map *m, bool shifted, DevMap &d) {
+  MapGeom g;
+  map_geom(m->grid, g);
+  d.d = m->d;
+  for (int i = 0; i < 16; ++i) d.inv[i] = shifted ? g.inv1[i] : g.inv0[i];
+  d.nx = g.nx; d.ny = g.ny; d.nz = g.nz;
+}
+static void to_dev(const vt_grid &grid, DevCoord &c) {
+  CoordGeom g;
+  coord_geom(grid, g);
+  c.ox = g.origin[0]; c.oy = g.origin[1]; c.oz = g.origin[2];
+  for (int k = 0; k < 3; ++k) { c.xd[k] = g.xd[k]; c.yd[k] = g.yd[k]; c.zd[k] = g.zd[k]; }
+  c.nx = g.nx; c.ny = g.ny; c.nz = g.nz;
+}
+
+// ------------------------------------------------------------------------------------------ generic CC
+__global__ void __launch_bounds__(kThreads) cc_generic_kernel(DevMap A, DevMap B, DevCoord C, double thr,
+                                                              double *partials, unsigned int *ticket, double *out) {
+  __shared__ double sm[6 * 32];
+  double acc[6] = {0, 0, 0, 0, 0, 0};  // sumA sumB sumAA sumBB sumAB count
+  const long rows = (long)C.ny * C.nz;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int gy = (int)(row % C.ny), gz = (int)(row / C.ny);
+    for (int gx = threadIdx.x; gx < C.nx; gx += blockDim.x) {
+      float x, y, z;
+      voxel_coord(C, gx, gy, gz, x, y, z);
+      const float vA = sample_interp<false>(A, x, y, z);
+      if (is_nan_bits(vA) || !((double)vA >= thr)) continue;  // MDFF.C:73-77 (B is only needed past this)
+      const float vB = sample_interp<false>(B, x, y, z);
+      if (is_nan_bits(vB)) continue;
+      acc[0] += (double)vA;
+      acc[1] += (double)vB;
+      acc[2] += (double)(vA * vA);
+      acc[3] += (double)(vB * vB);
+      acc[4] += (double)(vA * vB);
+      acc[5] += 1.0;
+    }
+  }
+  block_sum<6>(acc, sm);
+  grid_finish<6>(acc, partials, ticket, out, sm);
+}
+
+// ------------------------------------------------------------------------------------------ separable path
+using geom::AxisEntry;
+using geom::diagonal_inverse;
+
+// Host: can the chain voxel_coord -> cart_to_voxel be split per axis with identical bits?
+// Requires (1) output cell axes with exact-zero off-diagonals, (2) an inverse whose off-diagonal
+// 3x3 terms and projective column are exact zeros with m[15] == 1 (geom::diagonal_inverse).
+static bool axis_aligned_out(const DevCoord &c) {
+  return c.xd[1] == 0.f && c.xd[2] == 0.f && c.yd[0] == 0.f && c.yd[2] == 0.f && c.zd[0] == 0.f && c.zd[1] == 0.f;
+}
+
+static void build_axis(const DevCoord &c, int axis, const float *inv, int n_src, int n_out, std::vector<AxisEntry> &tab) {
+  tab.resize(n_out > 0 ? n_out : 1);
+  const double o = axis == 0 ? c.ox : (axis == 1 ? c.oy : c.oz);
+  const float delta = axis == 0 ? c.xd[0] : (axis == 1 ? c.yd[1] : c.zd[2]);
+  for (int g = 0; g < n_out; ++g) tab[g] = geom::axis_entry(axis, g, o, delta, inv[5 * axis], inv[12 + axis], n_src);
+}
+
+// The split is only bit-identical if the foreign-axis cartesian coordinates cannot leak in:
+// with exact-zero off-diagonals the products are +-0 unless a coordinate is inf/NaN.
+static bool finite_geom(const DevCoord &c) {
+  return std::isfinite(c.ox) && std::isfinite(c.oy) && std::isfinite(c.oz) && std::isfinite(c.xd[0]) &&
+         std::isfinite(c.yd[1]) && std::isfinite(c.zd[2]);
+}
+
+struct SepTables {
+  AxisEntry *d = nullptr;  // [Ax | Ay | Az | Bx | By | Bz]
+  int offAx, offAy, offAz, offBx, offBy, offBz;
+};
+
+static int upload_tables(const DevCoord &C, const DevMap &A, const DevMap &B, SepTables &T) {
+  std::vector<AxisEntry> all, t;
+  const DevMap *maps[2] = {&A, &B};
+  int offs[6];
+  for (int m = 0; m < 2; ++m) {
+    const int nsrc[3] = {maps[m]->nx, maps[m]->ny, maps[m]->nz};
+    const int nout[3] = {C.nx, C.ny, C.nz};
+    for (int ax = 0; ax < 3; ++ax) {
+      build_axis(C, ax, maps[m]->inv, nsrc[ax], nout[ax], t);
+      offs[m * 3 + ax] = (int)all.size();
+      all.insert(all.end(), t.begin(), t.begin() + (nout[ax] > 0 ? nout[ax] : 0));
+    }
+  }
+  T.offAx = offs[0]; T.offAy = offs[1]; T.offAz = offs[2];
+  T.offBx = offs[3]; T.offBy = offs[4]; T.offBz = offs[5];
+  if (dev_alloc((void **)&T.d, sizeof(AxisEntry) * (all.size() + 1))) return 2;
+  VT_CUDA(cudaMemcpyAsync(T.d, all.data(), sizeof(AxisEntry) * all.size(), cudaMemcpyHostToDevice, ctx().stream));
+  VT_CUDA(cudaStreamSynchronize(ctx().stream));  // `all` is pageable and about to go out of scope
+  return 0;
+}
+
+constexpr int kZChunk = 16;  // z steps per thread per work item
+
+__global__ void __launch_bounds__(kThreads) cc_sep_kernel(DevMap A, DevMap B, int nx, int ny, int nz,
+                                                          const AxisEntry *__restrict__ T, int offAx, int offAy,
+                                                          int offAz, int offBx, int offBy, int offBz, double thr,
+                                                          double *partials, unsigned int *ticket, double *out) {
+  __shared__ double sm[6 * 32];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  // work item = (32-wide x tile, gy, z chunk), dealt to warps round-robin (x tile fastest)
+  const int xtiles = (nx + 31) >> 5;
+  const int zchunks = (nz + kZChunk - 1) / kZChunk;
+  const long work = (long)xtiles * ny * zchunks;
+  const long planeA = (long)A.nx * A.ny, planeB = (long)B.nx * B.ny;
+  const int lane = threadIdx.x & 31;
+  const long wstride = (long)gridDim.x * (kThreads / 32);
+  for (long w = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); w < work; w += wstride) {
+    const int xb = (int)(w % xtiles);
+    const long r = w / xtiles;
+    const int gy = (int)(r % ny), zc = (int)(r / ny);
+    const int gx = xb * 32 + lane;
+    if (gx >= nx) continue;
+    const AxisEntry ax = T[offAx + gx], ay = T[offAy + gy];
+    const AxisEntry bx = T[offBx + gx], by = T[offBy + gy];
+    const bool inA = ax.inside && ay.inside, inB = bx.inside && by.inside;
+    if (!inA || !inB) continue;  // one of the samples would be NaN for every z
+    const long a_row0 = (long)ay.i0 * A.nx, a_row1 = (long)ay.i1 * A.nx;
+    const long b_row0 = (long)by.i0 * B.nx, b_row1 = (long)by.i1 * B.nx;
+    PlaneCache pa, pb;
+    float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;  // f32 within a chunk of <= 16, then f64
+    int cnt = 0;
+    const int zend = min(nz, (zc + 1) * kZChunk);
+    for (int gz = zc * kZChunk; gz < zend; ++gz) {
+      const AxisEntry az = T[offAz + gz], bz = T[offBz + gz];
+      if (!az.inside || !bz.inside) continue;
+      const float vA = sep_sample(A.d, planeA, a_row0, a_row1, ax.i0, ax.i1, ax.f, ay.f, az, pa);
+      if (is_nan_bits(vA) || !((double)vA >= thr)) continue;
+      const float vB = sep_sample(B.d, planeB, b_row0, b_row1, bx.i0, bx.i1, bx.f, by.f, bz, pb);
+      if (is_nan_bits(vB)) continue;
+      fA += vA; fB += vB; fAA += vA * vA; fBB += vB * vB; fAB += vA * vB;
+      ++cnt;
+    }
+    acc[0] += (double)fA; acc[1] += (double)fB; acc[2] += (double)fAA; acc[3] += (double)fBB; acc[4] += (double)fAB;
+    acc[5] += (double)cnt;
+  }
+  block_sum<6>(acc, sm);
+  grid_finish<6>(acc, partials, ticket, out, sm);
+}
+
+int k_cc(const vt_map *A, const vt_map *B, double thr, double sums[5], long *n) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  vt_grid og;
+  intersection_grid(A->grid, B->grid, og);  // MDFF.C:132
+  DevMap dA, dB;
+  DevCoord dC;
+  to_dev(A, false, dA);
+  to_dev(B, false, dB);
+  to_dev(og, dC);
+  const long vox = (long)og.xsize * og.ysize * og.zsize;
+  double *dout = c.d_scratch;
+  double *partials = c.d_scratch + 8;
+  if (vox <= 0 || og.xsize <= 0 || og.ysize <= 0 || og.zsize <= 0) {
+    for (int k = 0; k < 5; ++k) sums[k] = 0.0;
+    *n = 0;
+    return 0;
+  }
+  const bool sep = axis_aligned_out(dC) && diagonal_inverse(dA.inv) && diagonal_inverse(dB.inv) && finite_geom(dC) &&
+                   !getenv("VOLTOOL_FORCE_GENERIC");
+  if (sep) {
+    SepTables T;
+    int rc = upload_tables(dC, dA, dB, T);
+    if (rc) return rc;
+    const long work = (long)((og.xsize + 31) / 32) * og.ysize * ((og.zsize + kZChunk - 1) / kZChunk);
+    const long wblocks = (work + kThreads / 32 - 1) / (kThreads / 32);
+    int grid = (int)(wblocks < (long)c.sm_count * 8 ? wblocks : (long)c.sm_count * 8);
+    cc_sep_kernel<<<grid, kThreads, 0, c.stream>>>(dA, dB, og.xsize, og.ysize, og.zsize, T.d, T.offAx, T.offAy, T.offAz,
+                                                   T.offBx, T.offBy, T.offBz, thr, partials, c.d_ticket, dout);
+    VT_LAUNCHED();
+    dev_free(T.d);
+  } else {
+    const long rows = (long)og.ysize * og.zsize;
+    int grid = (int)(rows < (long)c.sm_count * 8 ? rows : (long)c.sm_count * 8);
+    cc_generic_kernel<<<grid, kThreads, 0, c.stream>>>(dA, dB, dC, thr, partials, c.d_ticket, dout);
+    VT_LAUNCHED();
+  }
+  VT_CUDA(cudaMemcpyAsync(c.h_pinned, dout, 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  VT_CUDA(cudaStreamSynchronize(c.stream));
+  for (int k = 0; k < 5; ++k) sums[k] = c.h_pinned[k];
+  *n = (long)c.h_pinned[5];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ two-map ops
+template <int OP, bool INTERP, bool UNION>
+__global__ void __launch_bounds__(kThreads) binary_kernel(DevMap A, DevMap B, DevCoord C, float *__restrict__ out) {
+  const long rows = (long)C.ny * C.nz;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int gy = (int)(row % C.ny), gz = (int)(row / C.ny);
+    for (int gx = threadIdx.x; gx < C.nx; gx += blockDim.x) {
+      float x, y, z;
+      voxel_coord(C, gx, gy, gz, x, y, z);
+      float r;
+      if (OP == VT_MULTIPLY) {  // NaN-returning lookups, Voltool.C:303-350
+        const float vA = INTERP ? sample_interp<false>(A, x, y, z) : sample_nearest<false>(A, x, y, z);
+        const float vB = INTERP ? sample_interp<false>(B, x, y, z) : sample_nearest<false>(B, x, y, z);
+        if (UNION) {
+          const bool na = is_nan_bits(vA), nb = is_nan_bits(vB);
+          r = (!na && !nb) ? vA * vB : (!na ? vA : (!nb ? vB : 0.0f));
+        } else {
+          r = vA * vB;
+        }
+      } else {  // zero outside, Voltool.C:249-300, 352-377
+        const float vA = INTERP ? sample_interp<true>(A, x, y, z) : sample_nearest<true>(A, x, y, z);
+        const float vB = INTERP ? sample_interp<true>(B, x, y, z) : sample_nearest<true>(B, x, y, z);
+        if (OP == VT_ADD) r = vA + vB;
+        else if (OP == VT_SUBTRACT) r = vA - vB;
+        else r = (float)((double)(vA + vB) * 0.5);
+      }
+      out[row * C.nx + gx] = r;
+    }
+  }
+}
+
+template <int OP>
+static void launch_binary(int interp, int use_union, int grid, const DevMap &A, const DevMap &B, const DevCoord &C,
+                          float *out) {
+  cudaStream_t s = ctx().stream;
+  if (interp) {
+    if (use_union) binary_kernel<OP, true, true><<<grid, kThreads, 0, s>>>(A, B, C, out);
+    else binary_kernel<OP, true, false><<<grid, kThreads, 0, s>>>(A, B, C, out);
+  } else {
+    if (use_union) binary_kernel<OP, false, true><<<grid, kThreads, 0, s>>>(A, B, C, out);
+    else binary_kernel<OP, false, false><<<grid, kThreads, 0, s>>>(A, B, C, out);
+  }
+}
+
+int k_binary(int op, int interp, int use_union, const vt_map *A, const vt_map *B, const vt_grid &og, float *out) {
+  VT_REQUIRE_CTX();
+  DevMap dA, dB;
+  DevCoord dC;
+  to_dev(A, !interp, dA);
+  to_dev(B, !interp, dB);
+  to_dev(og, dC);
+  const long rows = (long)og.ysize * og.zsize;
+  if (rows <= 0 || og.xsize <= 0) return 0;
+  int grid = (int)(rows < (long)ctx().sm_count * 8 ? rows : (long)ctx().sm_count * 8);
+  switch (op) {
+    case VT_ADD: launch_binary<VT_ADD>(interp, use_union, grid, dA, dB, dC, out); break;
+    case VT_SUBTRACT: launch_binary<VT_SUBTRACT>(interp, use_union, grid, dA, dB, dC, out); break;
+    case VT_MULTIPLY: launch_binary<VT_MULTIPLY>(interp, use_union, grid, dA, dB, dC, out); break;
+    case VT_AVERAGE: launch_binary<VT_AVERAGE>(interp, use_union, grid, dA, dB, dC, out); break;
+    default: set_error("vt_binary: unknown op %d", op); return 1;
+  }
+  VT_LAUNCHED();
+  return 0;
+}
+
+}  // namespace vt

@@ -1,0 +1,318 @@
+// vt_fit.cu -- C ABI of sim / calc_cc / fit over the batched pose pipeline (vt_sim.cu).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "vt_pose.cuh"
+
+using namespace vt;
+
+struct vt_fit_ctx {
+  AtomSet as;
+  PoseBatch pb;
+  const vt_map *target = nullptr;
+  float resolution = 0.f;
+  double threshold = 0.1;  // calc_cc hard-codes thresholddensity = 0.1 (TclVoltool.C:77)
+  int B = 0;
+  PrepPose *h_prep = nullptr;  // pinned staging, B entries
+  float *d_cc = nullptr;       // results of the current call
+  long cc_cap = 0;
+};
+
+namespace {
+
+SimParams make_params(int quality, float radscale, float gspacing) {
+  SimParams p;
+  p.radscale = radscale;
+  p.gs = gspacing;
+  p.invgs = 1.0f / gspacing;
+  p.gausslim = gausslim_for_quality(quality);
+  p.quality = quality;
+  return p;
+}
+
+// single structure, identity pose -> resident map (QuickSurf::calc_density_map)
+int sim_to_map(const float *pos, const float *radii, long natoms, int quality, float radscale, float gspacing,
+               bool want_minmax, vt_map **out) {
+  VT_REQUIRE_CTX();
+  if (!pos || !radii || natoms <= 0 || !(gspacing > 0.f)) { set_error("vt_sim: bad arguments"); return 1; }
+  AtomSet as;
+  int rc = atomset_create(pos, radii, natoms, make_params(quality, radscale, gspacing), as);
+  if (rc) return rc;
+  // exact grid size on the host (same float expressions as pose_setup_kernel) to size the slot
+  float mn[3] = {pos[0], pos[1], pos[2]}, mx[3] = {pos[0], pos[1], pos[2]};
+  for (long i = 0; i < natoms; ++i)
+    for (int k = 0; k < 3; ++k) {
+      const float v = pos[3 * i + k];
+      if (v < mn[k]) mn[k] = v;
+      if (v > mx[k]) mx[k] = v;
+    }
+  int nv[3];
+  long cells = 1;
+  int maxn = 0;
+  for (int k = 0; k < 3; ++k) {
+    const float lo = mn[k] - as.pad, hi = mx[k] + as.pad;
+    const float ax = hi - lo;
+    nv[k] = (int)std::ceil((double)(ax / gspacing));
+    if (nv[k] < 2) { atomset_destroy(as); set_error("vt_sim: degenerate grid"); return 1; }
+    cells *= nv[k];
+    if (nv[k] > maxn) maxn = nv[k];
+  }
+  PoseBatch pb;
+  pb.B = 1;
+  pb.cap_n = maxn;
+  pb.cap_grid = cells;
+  Ctx &c = ctx();
+  rc = dev_alloc((void **)&pb.d_tpos, sizeof(float4) * (size_t)as.n);
+  if (!rc) rc = dev_alloc((void **)&pb.d_tgroup, sizeof(float4) * (size_t)as.ngroups);
+  if (!rc) rc = dev_alloc((void **)&pb.d_bbox, sizeof(unsigned int) * 6);
+  if (!rc) rc = dev_alloc((void **)&pb.d_geom, sizeof(PoseGeom));
+  if (!rc) rc = dev_alloc((void **)&pb.d_totals, sizeof(int) * 4);
+  if (!rc) rc = dev_alloc((void **)&pb.d_grid, sizeof(float) * (size_t)cells);
+  const float com0[3] = {0.f, 0.f, 0.f};
+  if (!rc) rc = batch_prepare(as, pb, 1, nullptr, com0, 1, nullptr);
+  if (!rc) rc = batch_splat(as, pb, 1);
+  PoseGeom G;
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(&G, pb.d_geom, sizeof(G), cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "sim readback", __FILE__, __LINE__);
+  }
+  if (!rc && (G.nv[0] != nv[0] || G.nv[1] != nv[1] || G.nv[2] != nv[2])) {
+    set_error("vt_sim: host/device grid mismatch (%d %d %d vs %d %d %d)", nv[0], nv[1], nv[2], G.nv[0], G.nv[1], G.nv[2]);
+    rc = 3;
+  }
+  if (!rc) {
+    vt_map *m = new vt_map();
+    memset(&m->grid, 0, sizeof(m->grid));
+    for (int k = 0; k < 3; ++k) m->grid.origin[k] = (double)G.org[k];
+    m->grid.xaxis[0] = (double)((float)(nv[0] - 1) * gspacing);
+    m->grid.yaxis[1] = (double)((float)(nv[1] - 1) * gspacing);
+    m->grid.zaxis[2] = (double)((float)(nv[2] - 1) * gspacing);
+    m->grid.xsize = nv[0]; m->grid.ysize = nv[1]; m->grid.zsize = nv[2];
+    m->n = cells;
+    m->d = pb.d_grid;  // adopt the slot
+    pb.d_grid = nullptr;
+    memset(&m->cache, 0, sizeof(m->cache));
+    if (want_minmax) {
+      rc = k_minmax(m->d, m->n, &m->cache.cmin, &m->cache.cmax);
+      m->cache.minmax_valid = 1;
+    }
+    *out = m;
+  }
+  batch_destroy(pb);
+  atomset_destroy(as);
+  return rc;
+}
+
+__global__ void prep_from_pose_kernel(const vt_pose *__restrict__ poses, int n, PrepPose *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const vt_pose q = poses[i];
+  PrepPose r;
+  for (int k = 0; k < 3; ++k) {
+    // DEGTORAD in double, rotate_axis takes a float angle, cos/sin evaluated in double
+    const double amount = (double)q.rot_deg[k] * 3.14159265358979323846 / 180.0;
+    const float a = (float)amount;
+    r.c[k] = (float)cos((double)a);
+    r.s[k] = (float)sin((double)a);
+    r.shift[k] = q.shift[k];
+  }
+  out[i] = r;
+}
+
+int ensure_cc_buffer(vt_fit_ctx *f, long n) {
+  if (n <= f->cc_cap) return 0;
+  dev_free(f->d_cc);
+  f->d_cc = nullptr;
+  if (dev_alloc((void **)&f->d_cc, sizeof(float) * (size_t)n)) return 2;
+  f->cc_cap = n;
+  return 0;
+}
+
+// run the pipeline for poses already prepared on the device
+int eval_prepared(vt_fit_ctx *f, const float com[3], const PrepPose *d_prep, int n, float *d_cc) {
+  int rc = batch_prepare(f->as, f->pb, n, d_prep, com, 0, &f->target->grid);
+  if (!rc) rc = batch_splat(f->as, f->pb, n);
+  if (!rc) rc = batch_cc(f->pb, n, f->target, f->threshold, d_cc, nullptr);
+  return rc;
+}
+
+int cuda_table_eval(void *user, const float *origin_pos, const float com[3], int stride, int max_rot, int first,
+                    int step, float *table) {
+  vt_fit_ctx *f = (vt_fit_ctx *)user;
+  int rc = vt_fit_set_origin(f, origin_pos);
+  if (rc) return rc;
+  return vt_fit_rotate_table(f, com, stride, max_rot, first, step, table);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vt_sim(const float *pos, const float *radii, long natoms, int quality, float radscale, float gspacing,
+           vt_map **out) {
+  return sim_to_map(pos, radii, natoms, quality, radscale, gspacing, true, out);
+}
+
+int vt_calc_cc(const float *pos, const float *radii, long natoms, const vt_map *target, float resolution, double *cc) {
+  VT_REQUIRE_CTX();
+  float radscale;
+  double gspacing;
+  int quality;
+  // calc_cc: radscale = .2*res; gspacing = 1.5*radscale; threshold 0.1 (TclVoltool.C:77-88)
+  radscale = (float)(.2 * resolution);
+  gspacing = 1.5 * radscale;
+  quality = resolution >= 9 ? 0 : 3;
+  vt_map *sim = nullptr;
+  int rc = sim_to_map(pos, radii, natoms, quality, radscale, (float)gspacing, false, &sim);
+  if (rc) return rc;
+  double c = 0.0;
+  rc = vt_cc(sim, target, 0.1, &c, nullptr, nullptr);
+  vt_map_destroy(sim);
+  if (rc) return rc;
+  float ret = 0;
+  ret += c;  // float return_cc += cc (TclVoltool.C:75,126)
+  *cc = ret;
+  return 0;
+}
+
+int vt_sim_cc(const float *pos, const float *radii, long natoms, double resolution, double gspacing_in,
+              const vt_map *target, double threshold, double *cc, vt_map **synth_out) {
+  VT_REQUIRE_CTX();
+  float radscale;
+  double gspacing;
+  int quality;
+  sim_policy(resolution, gspacing_in, radscale, gspacing, quality);
+  vt_map *sim = nullptr;
+  int rc = sim_to_map(pos, radii, natoms, quality, radscale, (float)gspacing, synth_out != nullptr, &sim);
+  if (rc) return rc;
+  rc = vt_cc(sim, target, threshold, cc, nullptr, nullptr);
+  if (synth_out && !rc) *synth_out = sim;
+  else vt_map_destroy(sim);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------ fit context
+int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_map *target, float resolution,
+                  vt_fit_ctx **out) {
+  VT_REQUIRE_CTX();
+  if (!pos || !radii || !target || natoms <= 0) { set_error("vt_fit_create: bad arguments"); return 1; }
+  vt_fit_ctx *f = new vt_fit_ctx();
+  f->target = target;
+  f->resolution = resolution;
+  const float radscale = (float)(.2 * resolution);
+  const double gspacing = 1.5 * radscale;
+  const int quality = resolution >= 9 ? 0 : 3;
+  int rc = atomset_create(pos, radii, natoms, make_params(quality, radscale, (float)gspacing), f->as);
+  if (rc) { delete f; return rc; }
+  const char *env = getenv("VOLTOOL_FIT_BATCH");
+  f->B = env ? atoi(env) : 128;
+  if (f->B < 1) f->B = 1;
+  if (f->B > 1024) f->B = 1024;
+  rc = batch_create(f->as, &target->grid, f->B, f->pb);
+  if (!rc) {
+    cudaError_t e = cudaMallocHost((void **)&f->h_prep, sizeof(PrepPose) * f->B);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+  }
+  if (rc) { vt_fit_destroy(f); return rc; }
+  *out = f;
+  return 0;
+}
+
+int vt_fit_destroy(vt_fit_ctx *f) {
+  if (!f) return 0;
+  cudaStreamSynchronize(ctx().stream);
+  batch_destroy(f->pb);
+  atomset_destroy(f->as);
+  dev_free(f->d_cc);
+  if (f->h_prep) cudaFreeHost(f->h_prep);
+  delete f;
+  return 0;
+}
+
+int vt_fit_set_origin(vt_fit_ctx *f, const float *pos) {
+  VT_REQUIRE_CTX();
+  return atomset_set_positions(f->as, pos);
+}
+
+int vt_fit_eval_poses(vt_fit_ctx *f, const float com[3], const vt_pose *poses, long nposes, float *cc_out) {
+  VT_REQUIRE_CTX();
+  if (nposes <= 0) return 0;
+  int rc = ensure_cc_buffer(f, nposes);
+  if (rc) return rc;
+  Ctx &c = ctx();
+  for (long p0 = 0; p0 < nposes; p0 += f->B) {
+    const int n = (int)std::min<long>(f->B, nposes - p0);
+    // the pinned staging buffer is reused: wait for the previous batch's upload to be consumed
+    VT_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < n; ++i) {
+      const vt_pose &q = poses[p0 + i];
+      for (int k = 0; k < 3; ++k) {
+        euler_cs((double)q.rot_deg[k], f->h_prep[i].c[k], f->h_prep[i].s[k]);
+        f->h_prep[i].shift[k] = q.shift[k];
+      }
+    }
+    VT_CUDA(cudaMemcpyAsync(f->pb.d_prep, f->h_prep, sizeof(PrepPose) * n, cudaMemcpyHostToDevice, c.stream));
+    rc = eval_prepared(f, com, f->pb.d_prep, n, f->d_cc + p0);
+    if (rc) return rc;
+  }
+  VT_CUDA(cudaMemcpyAsync(cc_out, f->d_cc, sizeof(float) * (size_t)nposes, cudaMemcpyDeviceToHost, c.stream));
+  VT_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int vt_fit_eval_poses_device(vt_fit_ctx *f, const float com[3], const vt_pose *d_poses, long nposes, float *d_cc) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  for (long p0 = 0; p0 < nposes; p0 += f->B) {
+    const int n = (int)std::min<long>(f->B, nposes - p0);
+    prep_from_pose_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(d_poses + p0, n, f->pb.d_prep);
+    VT_LAUNCHED();
+    int rc = eval_prepared(f, com, f->pb.d_prep, n, d_cc + p0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int vt_fit_rotate_table(vt_fit_ctx *f, const float com[3], int stride, int max_rot, int first, int step,
+                        float *table) {
+  VT_REQUIRE_CTX();
+  if (max_rot < 1 || step < 1 || first < 0) { set_error("vt_fit_rotate_table: bad arguments"); return 1; }
+  const int total = max_rot * max_rot * max_rot;
+  std::vector<vt_pose> poses;
+  std::vector<int> idx;
+  for (int i = first; i < total; i += step) {
+    vt_pose q;
+    q.rot_deg[0] = (float)(stride * (i / (max_rot * max_rot)));   // x outermost, TclVoltool.C:160-174
+    q.rot_deg[1] = (float)(stride * ((i / max_rot) % max_rot));
+    q.rot_deg[2] = (float)(stride * (i % max_rot));
+    q.shift[0] = q.shift[1] = q.shift[2] = 0.f;
+    poses.push_back(q);
+    idx.push_back(i);
+  }
+  std::vector<float> cc(poses.size());
+  int rc = vt_fit_eval_poses(f, com, poses.data(), (long)poses.size(), cc.data());
+  if (rc) return rc;
+  for (size_t k = 0; k < idx.size(); ++k) table[idx[k]] = cc[k];
+  return 0;
+}
+
+int vt_fit(float *pos, const float *radii, const float *mass, long natoms, const vt_map *target, float resolution,
+           vt_fit_result *res) {
+  VT_REQUIRE_CTX();
+  float dencom[3];
+  int rc = vt_vol_com(target, dencom);  // :799
+  if (rc) return rc;
+  // the evaluator context is created on the COM-aligned coordinates inside the schedule: build it
+  // on the input coordinates (the atom order/radii are what matter) and let set_origin refresh it
+  vt_fit_ctx *f = nullptr;
+  rc = vt_fit_create(pos, radii, natoms, target, resolution, &f);
+  if (rc) return rc;
+  rc = vt_fit_schedule(pos, mass, natoms, dencom, cuda_table_eval, f, res);
+  vt_fit_destroy(f);
+  return rc;
+}
+
+}  // extern "C"

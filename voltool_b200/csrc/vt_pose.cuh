@@ -1,0 +1,92 @@
+// vt_pose.cuh -- data structures of the batched pose pipeline (sim + cc for many rigid poses of one
+// atom set against one resident target map).
+#pragma once
+#include "vt_device.cuh"
+#include "vt_geom.h"
+
+namespace vt {
+
+// one candidate, host-prepared: cos/sin of the three Euler angles as the reference's do_rotate
+// forms them (TclVoltool.C:131-136), plus the extension translation
+struct PrepPose {
+  float c[3], s[3];
+  float shift[3];
+};
+
+struct SimParams {
+  float radscale, gs, invgs, gausslim;
+  int quality;
+};
+
+// splat tile (voxels) and staging sizes
+constexpr int kTX = 16, kTY = 16, kTZ = 8;
+constexpr int kChunk = 64;     // atoms staged per compute round
+constexpr int kRec = 44;       // floats per staged atom record
+constexpr int kMaxIds = 2048;  // gathered atom ids per flush
+constexpr int kZChunkFit = 16;
+
+// per-pose geometry, written by pose_setup_kernel
+struct PoseGeom {
+  float org[3];       // sim grid origin (float, as QuickSurf keeps it)
+  int nv[3];          // sim grid size
+  int no[3];          // intersection grid size (cc)
+  int valid;          // 0: cc undefined for this pose (empty intersection / capacity)
+  double oorg[3];     // intersection origin
+  float od[3];        // intersection cell deltas (diagonal)
+  float sinv_d[3];    // sim map inverse: diagonal
+  float sinv_t[3];    //                 translation
+  int tiles[3];
+  int tile_base;      // exclusive prefix of tile counts over the batch
+  int cc_items;       // warp work items of the cc stage
+  int cc_base;        // exclusive prefix
+  int cc_xt, cc_zc;
+};
+
+// resident atom set, sorted along a Morton curve and cut into groups of 32
+struct AtomSet {
+  int n = 0, ngroups = 0;
+  float4 *d_xyzr = nullptr;   // origin-frame coordinates + radius (sorted order)
+  float4 *d_const = nullptr;  // per atom: arinv, radlim^2, radlim/gs, radius
+  float4 *d_group = nullptr;  // per group: centre (origin frame) + reach
+  int *h_perm = nullptr;      // sorted position -> caller's atom index (host)
+  float *h_radii = nullptr;   // radii in the caller's order (host)
+  float maxrad = 0.f, pad = 0.f;
+  float bound_center[3] = {0, 0, 0};
+  float bound_radius = 0.f;   // all atoms within this distance of bound_center
+  SimParams prm{};
+};
+
+// workspace for a batch of B poses
+struct PoseBatch {
+  int B = 0;              // slots
+  int cap_n = 0;          // sim grid capacity per axis
+  long cap_grid = 0;      // floats per sim grid slot
+  int cap_o = 0;          // intersection capacity per axis
+  long cap_items = 0;     // cc work items capacity per pose
+  float4 *d_tpos = nullptr;
+  float4 *d_tgroup = nullptr;
+  unsigned int *d_bbox = nullptr;
+  PoseGeom *d_geom = nullptr;
+  int *d_totals = nullptr;  // [0] tiles, [1] cc items
+  float *d_grid = nullptr;
+  geom::AxisEntry *d_tab = nullptr;  // [B][6][cap_o]
+  double *d_part = nullptr;          // [B][cap_items][6]
+  PrepPose *d_prep = nullptr;        // [B]
+};
+
+int atomset_create(const float *pos, const float *radii, long n, const SimParams &prm, AtomSet &as);
+int atomset_set_positions(AtomSet &as, const float *pos);
+void atomset_destroy(AtomSet &as);
+
+int batch_create(const AtomSet &as, const vt_grid *target, int B, PoseBatch &pb);
+void batch_destroy(PoseBatch &pb);
+
+// stage 1: transform (or copy, identity != 0) + bbox + per-pose sim geometry (+ cc geometry if target)
+int batch_prepare(const AtomSet &as, PoseBatch &pb, int npose, const PrepPose *d_prep, const float com[3],
+                  int identity, const vt_grid *target);
+// stage 2: splat every pose's density grid
+int batch_splat(const AtomSet &as, PoseBatch &pb, int npose);
+// stage 3: cc of every pose's grid against the target; d_cc[npose] floats
+int batch_cc(PoseBatch &pb, int npose, const vt_map *target, double threshold, float *d_cc, double *d_sums);
+
+}  // namespace vt

@@ -1,0 +1,163 @@
+// vt_resample.cu -- pad/crop copy, 2x downsample, 2x cubic supersample.
+#include "vt_device.cuh"
+
+namespace vt {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------ pad
+// VolumetricData::pad copy loop (VolumetricData.C:560-574): the window [s,e) of the NEW grid is
+// filled from old voxel (g - pad_minus); everything else is zero.
+__global__ void __launch_bounds__(kThreads) pad_kernel(const float *__restrict__ src, int ox, int oy,
+                                                       float *__restrict__ dst, PadPlan p) {
+  const long rows = (long)p.ny * p.nz;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int gy = (int)(row % p.ny), gz = (int)(row / p.ny);
+    float *out = dst + row * p.nx;
+    const bool live = gy >= p.sy && gy < p.ey && gz >= p.sz && gz < p.ez;
+    const float *in = src + ((long)(gz - p.pzm) * oy + (gy - p.pym)) * (long)ox - p.pxm;
+    for (int gx = threadIdx.x; gx < p.nx; gx += blockDim.x)
+      out[gx] = (live && gx >= p.sx && gx < p.ex) ? in[gx] : 0.0f;
+  }
+}
+
+int k_pad_copy(const float *src, int ox, int oy, float *dst, const PadPlan &p) {
+  VT_REQUIRE_CTX();
+  long rows = (long)p.ny * p.nz;
+  int grid = (int)(rows < (long)ctx().sm_count * 16 ? rows : (long)ctx().sm_count * 16);
+  if (grid < 1) grid = 1;
+  pad_kernel<<<grid, kThreads, 0, ctx().stream>>>(src, ox, oy, dst, p);
+  VT_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ downsample
+// VolumetricData::downsample, VolumetricData.C:720-743: each new voxel is the double-precision
+// sum of its 2x2x2 block, added in the order (x, x+1) of row y, row y+1, then the same in plane
+// z+1, times the double 1/8.
+__global__ void __launch_bounds__(kThreads) downsample_kernel(const float *__restrict__ src, int ox, int oy,
+                                                              float *__restrict__ dst, int nx, int ny, int nz) {
+  const long rows = (long)ny * nz;
+  const long oxy = (long)ox * oy;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int gy = (int)(row % ny), gz = (int)(row / ny);
+    const float *b = src + 2L * gz * oxy + 2L * gy * ox;
+    for (int gx = threadIdx.x; gx < nx; gx += blockDim.x) {
+      const float2 r0 = __ldcs(reinterpret_cast<const float2 *>(b) + gx);
+      const float2 r1 = __ldcs(reinterpret_cast<const float2 *>(b + ox) + gx);
+      const float2 r2 = __ldcs(reinterpret_cast<const float2 *>(b + oxy) + gx);
+      const float2 r3 = __ldcs(reinterpret_cast<const float2 *>(b + oxy + ox) + gx);
+      double Z = 0.0;
+      Z += r0.x; Z += r0.y; Z += r1.x; Z += r1.y; Z += r2.x; Z += r2.y; Z += r3.x; Z += r3.y;
+      dst[row * nx + gx] = (float)(Z * 0.125);
+    }
+  }
+}
+
+// rows whose start is not 8-byte aligned (odd old x size) take the scalar path
+__global__ void __launch_bounds__(kThreads) downsample_kernel_scalar(const float *__restrict__ src, int ox, int oy,
+                                                                     float *__restrict__ dst, int nx, int ny, int nz) {
+  const long rows = (long)ny * nz;
+  const long oxy = (long)ox * oy;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int gy = (int)(row % ny), gz = (int)(row / ny);
+    const float *b = src + 2L * gz * oxy + 2L * gy * ox;
+    for (int gx = threadIdx.x; gx < nx; gx += blockDim.x) {
+      const float *q = b + 2 * gx;
+      double Z = 0.0;
+      Z += q[0]; Z += q[1]; Z += q[ox]; Z += q[ox + 1];
+      Z += q[oxy]; Z += q[oxy + 1]; Z += q[oxy + ox]; Z += q[oxy + ox + 1];
+      dst[row * nx + gx] = (float)(Z * 0.125);
+    }
+  }
+}
+
+int k_downsample(const float *src, int ox, int oy, int oz, float *dst) {
+  VT_REQUIRE_CTX();
+  const int nx = ox / 2, ny = oy / 2, nz = oz / 2;
+  long rows = (long)ny * nz;
+  if (rows < 1 || nx < 1) return 0;
+  int grid = (int)(rows < (long)ctx().sm_count * 16 ? rows : (long)ctx().sm_count * 16);
+  if ((ox & 1) == 0)
+    downsample_kernel<<<grid, kThreads, 0, ctx().stream>>>(src, ox, oy, dst, nx, ny, nz);
+  else
+    downsample_kernel_scalar<<<grid, kThreads, 0, ctx().stream>>>(src, ox, oy, dst, nx, ny, nz);
+  VT_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ supersample
+// VolumetricData::cubic_interp (VolumetricData.h:224-232) at mu = 1/2
+__device__ __forceinline__ float cubic_half(float y0, float y1, float y2, float y3) {
+  const float mu = 0.5f, mu2 = mu * mu;
+  const float a0 = y3 - y2 - y0 + y1;
+  const float a1 = y0 - y1 - a0;
+  const float a2 = y2 - y0;
+  return (a0 * mu * mu2 + a1 * mu2 + a2 * mu + y1);
+}
+
+// value at NEW x index X of an x-supersampled source row (VolumetricData.C:783-838): even X copy
+// the source; odd X = 2g+1 interpolate (g-1, g, g+1, g+2) with the end sample replicated
+__device__ __forceinline__ float xline(const float *__restrict__ row, int ox, int X) {
+  const int g = X >> 1;
+  if ((X & 1) == 0) return __ldg(row + g);
+  const int gm = g > 0 ? g - 1 : 0;
+  const int gp = g + 2 < ox ? g + 2 : ox - 1;
+  return cubic_half(__ldg(row + gm), __ldg(row + g), __ldg(row + g + 1), __ldg(row + gp));
+}
+
+// pass 1: every EVEN output plane (Z = 2gz): x then y interpolation (:783-875).  The y stencil is
+// evaluated on x-interpolated rows, exactly as the reference's in-place sweeps leave them.
+__global__ void __launch_bounds__(kThreads) supersample_xy_kernel(const float *__restrict__ src, int ox, int oy,
+                                                                  int oz, float *__restrict__ dst, int nx, int ny) {
+  const long rows = (long)ny * oz;
+  const long oxy = (long)ox * oy, nxy = (long)nx * ny;
+  for (long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int Y = (int)(r % ny), gz = (int)(r / ny);
+    const float *plane = src + gz * oxy;
+    float *out = dst + 2L * gz * nxy + (long)Y * nx;
+    const int g = Y >> 1;
+    if ((Y & 1) == 0) {
+      const float *row = plane + (long)g * ox;
+      for (int X = threadIdx.x; X < nx; X += blockDim.x) out[X] = xline(row, ox, X);
+    } else {
+      const int gm = g > 0 ? g - 1 : 0;
+      const int gp = g + 2 < oy ? g + 2 : oy - 1;
+      const float *r0 = plane + (long)gm * ox, *r1 = plane + (long)g * ox;
+      const float *r2 = plane + (long)(g + 1) * ox, *r3 = plane + (long)gp * ox;
+      for (int X = threadIdx.x; X < nx; X += blockDim.x)
+        out[X] = cubic_half(xline(r0, ox, X), xline(r1, ox, X), xline(r2, ox, X), xline(r3, ox, X));
+    }
+  }
+}
+
+// pass 2: every ODD output plane from the four surrounding even planes (:878-913)
+__global__ void __launch_bounds__(kThreads) supersample_z_kernel(float *__restrict__ dst, int nx, int ny, int oz) {
+  const long nxy = (long)nx * ny;
+  const long total = nxy * (oz - 1);
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int g = (int)(i / nxy);
+    const long r = i - (long)g * nxy;
+    const int gm = g > 0 ? g - 1 : 0;
+    const int gp = g + 2 < oz ? g + 2 : oz - 1;
+    const float v = cubic_half(dst[r + 2L * gm * nxy], dst[r + 2L * g * nxy], dst[r + 2L * (g + 1) * nxy],
+                               dst[r + 2L * gp * nxy]);
+    dst[r + (2L * g + 1) * nxy] = v;
+  }
+}
+
+int k_supersample(const float *src, int ox, int oy, int oz, float *dst) {
+  VT_REQUIRE_CTX();
+  if (ox < 3 || oy < 3 || oz < 3) { set_error("vt_supersample: every dimension must be >= 3"); return 1; }
+  const int nx = 2 * ox - 1, ny = 2 * oy - 1;
+  long rows = (long)ny * oz;
+  int grid = (int)(rows < (long)ctx().sm_count * 16 ? rows : (long)ctx().sm_count * 16);
+  supersample_xy_kernel<<<grid, kThreads, 0, ctx().stream>>>(src, ox, oy, oz, dst, nx, ny);
+  VT_LAUNCHED();
+  supersample_z_kernel<<<ctx().sm_count * 8, kThreads, 0, ctx().stream>>>(dst, nx, ny, oz);
+  VT_LAUNCHED();
+  return 0;
+}
+
+}  // namespace vt

@@ -1,0 +1,696 @@
+// vt_sim.cu -- the batched pose pipeline: rigid transform, bounding box, per-pose grid geometry,
+// Gaussian splat, and the per-pose cross correlation against the resident target map.
+//
+// Replaces, per candidate pose of fit's rotate() loop (TclVoltool.C:160-199):
+//   moveby / do_rotate x3 / moveby              TclVoltool.C:52-63, 131-136, 165-176
+//   QuickSurf::calc_density_map (CPU branch)    TclVoltool.C:119-122   (restated in oracle/)
+//   cc_threaded(sim, target, &cc, 0.1)          TclVoltool.C:124 -> MDFF.C:102-151
+// and, with a single identity pose, voltool sim / cc (TclMDFF.C:154-157, 496-524).
+//
+// Splat design (no atomics, no tensor cores: nothing here is a contraction):
+//   * atoms are sorted once along a Morton curve and cut into groups of 32 with a bounding sphere;
+//     groups are rigid, so a pose only moves their centres.
+//   * a CTA owns a 16x16x8-voxel tile.  It culls groups against the tile (thread per group), then
+//     tests the atoms of surviving groups exactly (warp per group, the reference's integer box),
+//     compacting ids in a fixed order through ballots + shared-memory offsets.
+//   * atoms are staged 64 at a time as separable records: Ex[16] = exp2(dx^2 * a) per tile column
+//     (0 outside the atom's x range), dy^2[16], dz^2[8] (+inf outside the y/z range), so the
+//     reference's cutoff test dy^2+dz^2 < (gausslim*sigma)^2 is evaluated on the same floats.
+//   * each thread owns 8 consecutive x voxels of one (y,z) in registers; a warp covers 8x8x4
+//     voxels and skips staged atoms whose box misses that region (8-bit mask per record).
+//     Per (thread, atom): one ex2 for the y-z factor and 8 FMAs.
+//   * every voxel is written exactly once (no memset, no read-modify-write).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "vt_pose.cuh"
+#include "vt_sep.cuh"
+
+namespace vt {
+
+constexpr float kLog2e = 1.44269504088896f;  // MLOG2EF of the oracle's splat
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// monotone float <-> uint key for atomicMin/atomicMax
+__device__ __forceinline__ unsigned int fkey(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ------------------------------------------------------------------------------------------ host: atom set
+static inline unsigned int spread10(unsigned int v) {
+  v &= 0x3ff;
+  v = (v | (v << 16)) & 0x030000FF;
+  v = (v | (v << 8)) & 0x0300F00F;
+  v = (v | (v << 4)) & 0x030C30C3;
+  v = (v | (v << 2)) & 0x09249249;
+  return v;
+}
+
+static void group_spheres(const AtomSet &as, const std::vector<float4> &xyzr, std::vector<float4> &groups) {
+  groups.resize(as.ngroups);
+  for (int g = 0; g < as.ngroups; ++g) {
+    const int a0 = g * 32, a1 = std::min(as.n, a0 + 32);
+    float lo[3] = {xyzr[a0].x, xyzr[a0].y, xyzr[a0].z}, hi[3] = {lo[0], lo[1], lo[2]};
+    float maxcut = 0.f;
+    for (int i = a0; i < a1; ++i) {
+      const float p[3] = {xyzr[i].x, xyzr[i].y, xyzr[i].z};
+      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); }
+      maxcut = std::max(maxcut, as.prm.gausslim * xyzr[i].w * as.prm.radscale);
+    }
+    const float c[3] = {0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), 0.5f * (lo[2] + hi[2])};
+    float r2 = 0.f;
+    for (int i = a0; i < a1; ++i) {
+      const float dx = xyzr[i].x - c[0], dy = xyzr[i].y - c[1], dz = xyzr[i].z - c[2];
+      r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+    }
+    // reach = sphere radius + largest cutoff + slack for float rounding of the rigid transform
+    const float reach = std::sqrt(r2) + maxcut + 0.05f + 1e-4f * (std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]));
+    groups[g] = make_float4(c[0], c[1], c[2], reach);
+  }
+}
+
+static int upload_positions(AtomSet &as, const float *pos, const float *radii_sorted_src, bool first) {
+  std::vector<float4> xyzr(as.n);
+  for (int i = 0; i < as.n; ++i) {
+    const int o = as.h_perm[i];
+    xyzr[i] = make_float4(pos[3 * o], pos[3 * o + 1], pos[3 * o + 2], radii_sorted_src[o]);
+  }
+  std::vector<float4> groups;
+  group_spheres(as, xyzr, groups);
+  // bounding sphere of everything (capacity planning)
+  double c[3] = {0, 0, 0};
+  for (int i = 0; i < as.n; ++i) { c[0] += xyzr[i].x; c[1] += xyzr[i].y; c[2] += xyzr[i].z; }
+  for (int k = 0; k < 3; ++k) as.bound_center[k] = (float)(c[k] / std::max(1, as.n));
+  double r2 = 0;
+  for (int i = 0; i < as.n; ++i) {
+    const double dx = xyzr[i].x - as.bound_center[0], dy = xyzr[i].y - as.bound_center[1], dz = xyzr[i].z - as.bound_center[2];
+    r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+  }
+  as.bound_radius = (float)std::sqrt(r2);
+  cudaStream_t s = ctx().stream;
+  VT_CUDA(cudaMemcpyAsync(as.d_xyzr, xyzr.data(), sizeof(float4) * as.n, cudaMemcpyHostToDevice, s));
+  VT_CUDA(cudaMemcpyAsync(as.d_group, groups.data(), sizeof(float4) * as.ngroups, cudaMemcpyHostToDevice, s));
+  if (first) {
+    std::vector<float4> cst(as.n);
+    const float invgs = as.prm.invgs;
+    for (int i = 0; i < as.n; ++i) {
+      // per-atom constants of the oracle's splat_range
+      const float scaledrad = xyzr[i].w * as.prm.radscale;
+      const float arinv = -(1.0f / (2.0f * scaledrad * scaledrad)) * kLog2e;
+      float radlim = as.prm.gausslim * scaledrad;
+      const float radlim2 = radlim * radlim;
+      radlim *= invgs;
+      cst[i] = make_float4(arinv, radlim2, radlim, xyzr[i].w);
+    }
+    VT_CUDA(cudaMemcpyAsync(as.d_const, cst.data(), sizeof(float4) * as.n, cudaMemcpyHostToDevice, s));
+  }
+  VT_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int atomset_create(const float *pos, const float *radii, long n, const SimParams &prm, AtomSet &as) {
+  VT_REQUIRE_CTX();
+  if (n <= 0) { set_error("atom set is empty"); return 1; }
+  as.n = (int)n;
+  as.ngroups = (as.n + 31) / 32;
+  as.prm = prm;
+  // Morton order over 2^10 cells per axis
+  float lo[3] = {pos[0], pos[1], pos[2]}, hi[3] = {pos[0], pos[1], pos[2]};
+  float maxrad = radii[0];
+  for (long i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], pos[3 * i + k]); hi[k] = std::max(hi[k], pos[3 * i + k]); }
+    maxrad = std::max(maxrad, radii[i]);
+  }
+  as.maxrad = maxrad;
+  as.pad = sim_padding(prm.radscale, maxrad);
+  const float ext = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), std::max(hi[2] - lo[2], 1e-3f));
+  const float q = 1023.0f / ext;
+  std::vector<std::pair<unsigned int, int>> keys(n);
+  for (long i = 0; i < n; ++i) {
+    unsigned int code = 0;
+    for (int k = 0; k < 3; ++k) {
+      int c = (int)((pos[3 * i + k] - lo[k]) * q);
+      c = std::min(1023, std::max(0, c));
+      code |= spread10((unsigned int)c) << k;
+    }
+    keys[i] = {code, (int)i};
+  }
+  std::sort(keys.begin(), keys.end());
+  as.h_perm = new int[n];
+  as.h_radii = new float[n];
+  memcpy(as.h_radii, radii, sizeof(float) * n);
+  for (long i = 0; i < n; ++i) as.h_perm[i] = keys[i].second;
+  if (dev_alloc((void **)&as.d_xyzr, sizeof(float4) * n)) return 2;
+  if (dev_alloc((void **)&as.d_const, sizeof(float4) * n)) return 2;
+  if (dev_alloc((void **)&as.d_group, sizeof(float4) * as.ngroups)) return 2;
+  return upload_positions(as, pos, radii, true);
+}
+
+int atomset_set_positions(AtomSet &as, const float *pos) { return upload_positions(as, pos, as.h_radii, false); }
+
+void atomset_destroy(AtomSet &as) {
+  dev_free(as.d_xyzr); dev_free(as.d_const); dev_free(as.d_group);
+  delete[] as.h_perm;
+  delete[] as.h_radii;
+  as = AtomSet();
+}
+
+// ------------------------------------------------------------------------------------------ batch workspace
+int batch_create(const AtomSet &as, const vt_grid *target, int B, PoseBatch &pb) {
+  VT_REQUIRE_CTX();
+  pb.B = B;
+  const float gs = as.prm.gs;
+  // any rigid pose keeps the atoms inside the bounding sphere: extent <= 2R + 2 pad (+ shift slack)
+  const double ext = 2.0 * as.bound_radius + 2.0 * as.pad + 4.0 * gs;
+  pb.cap_n = (int)std::ceil(ext / gs) + 2;
+  pb.cap_grid = (long)pb.cap_n * pb.cap_n * pb.cap_n;
+  if (target) {
+    double dens = 1.15 / gs;
+    const double la[3] = {target->xaxis[0], target->yaxis[1], target->zaxis[2]};
+    const int na[3] = {target->xsize, target->ysize, target->zsize};
+    double maxlen = 0;
+    for (int k = 0; k < 3; ++k) {
+      if (la[k] > 0) dens = std::max(dens, na[k] / la[k]);
+      maxlen = std::max(maxlen, std::min(la[k], (double)pb.cap_n * gs));
+    }
+    pb.cap_o = (int)(maxlen * dens * 1.01) + 8;
+    pb.cap_items = (long)((pb.cap_o + 31) / 32) * pb.cap_o * ((pb.cap_o + kZChunkFit - 1) / kZChunkFit);
+  } else {
+    pb.cap_o = 0;
+    pb.cap_items = 0;
+  }
+  if (dev_alloc((void **)&pb.d_tpos, sizeof(float4) * (size_t)B * as.n)) return 2;
+  if (dev_alloc((void **)&pb.d_tgroup, sizeof(float4) * (size_t)B * as.ngroups)) return 2;
+  if (dev_alloc((void **)&pb.d_bbox, sizeof(unsigned int) * 6 * B)) return 2;
+  if (dev_alloc((void **)&pb.d_geom, sizeof(PoseGeom) * B)) return 2;
+  if (dev_alloc((void **)&pb.d_totals, sizeof(int) * 4)) return 2;
+  if (dev_alloc((void **)&pb.d_grid, sizeof(float) * (size_t)B * pb.cap_grid)) return 2;
+  if (dev_alloc((void **)&pb.d_prep, sizeof(PrepPose) * B)) return 2;
+  if (target) {
+    if (dev_alloc((void **)&pb.d_tab, sizeof(geom::AxisEntry) * (size_t)B * 6 * pb.cap_o)) return 2;
+    if (dev_alloc((void **)&pb.d_part, sizeof(double) * 6 * (size_t)B * pb.cap_items)) return 2;
+  }
+  return 0;
+}
+
+void batch_destroy(PoseBatch &pb) {
+  dev_free(pb.d_tpos); dev_free(pb.d_tgroup); dev_free(pb.d_bbox); dev_free(pb.d_geom); dev_free(pb.d_totals);
+  dev_free(pb.d_grid); dev_free(pb.d_prep); dev_free(pb.d_tab); dev_free(pb.d_part);
+  pb = PoseBatch();
+}
+
+// ------------------------------------------------------------------------------------------ transform + bbox
+// Matrix4::multpoint3d with the axis rotations of do_rotate (w = 1, zero translation).  Terms that
+// are an exact zero (coordinate * 0, + 0) are dropped: they can only flip the sign of a zero
+// result.  Every surviving product and sum rounds as in the reference (--fmad=false).
+__device__ __forceinline__ float3 rigid_pose(float3 p, const PrepPose &q, float3 com) {
+  // moveby(-com): TclVoltool.C:157,165
+  p.x = p.x + (-1.0f * com.x); p.y = p.y + (-1.0f * com.y); p.z = p.z + (-1.0f * com.z);
+  // about X (m5=c m6=s m9=-s m10=c): y' = (x*0 + y*c) + z*(-s); z' = (x*0 + y*s) + z*c
+  { const float c = q.c[0], s = q.s[0];
+    const float ny = p.y * c + p.z * (-s), nz = p.y * s + p.z * c;
+    p.y = ny; p.z = nz; }
+  // about Y (m0=c m2=-s m8=s m10=c): x' = (x*c + y*0) + z*s; z' = (x*(-s) + y*0) + z*c
+  { const float c = q.c[1], s = q.s[1];
+    const float nx = p.x * c + p.z * s, nz = p.x * (-s) + p.z * c;
+    p.x = nx; p.z = nz; }
+  // about Z (m0=c m1=s m4=-s m5=c): x' = (x*c + y*(-s)) + z*0; y' = (x*s + y*c) + z*0
+  { const float c = q.c[2], s = q.s[2];
+    const float nx = p.x * c + p.y * (-s), ny = p.x * s + p.y * c;
+    p.x = nx; p.y = ny; }
+  p.x = p.x + com.x; p.y = p.y + com.y; p.z = p.z + com.z;             // moveby(+com) :176
+  p.x = p.x + q.shift[0]; p.y = p.y + q.shift[1]; p.z = p.z + q.shift[2];
+  return p;
+}
+
+__global__ void bbox_reset_kernel(unsigned int *bbox, int npose) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npose * 6) bbox[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
+}
+
+__global__ void __launch_bounds__(256) transform_kernel(const float4 *__restrict__ xyzr, const float4 *__restrict__ groups,
+                                                        int n, int ngroups, const PrepPose *__restrict__ prep,
+                                                        float3 com, int identity, float4 *__restrict__ tpos,
+                                                        float4 *__restrict__ tgroup, unsigned int *__restrict__ bbox) {
+  const int pose = blockIdx.y;
+  PrepPose q;
+  if (!identity) q = prep[pose];
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 a = xyzr[i];
+    float3 p = make_float3(a.x, a.y, a.z);
+    if (!identity) p = rigid_pose(p, q, com);
+    tpos[(size_t)pose * n + i] = make_float4(p.x, p.y, p.z, a.w);
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+    const float4 c = groups[g];
+    float3 p = make_float3(c.x, c.y, c.z);
+    if (!identity) p = rigid_pose(p, q, com);
+    tgroup[(size_t)pose * ngroups + g] = make_float4(p.x, p.y, p.z, c.w);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (mn[k] <= mx[k]) {
+        atomicMin(&bbox[pose * 6 + k], fkey(mn[k]));
+        atomicMax(&bbox[pose * 6 + 3 + k], fkey(mx[k]));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ per-pose geometry
+struct TargetGeom {
+  vt_grid grid;
+  float inv[16];
+  int present;
+};
+
+__global__ void pose_setup_kernel(const unsigned int *__restrict__ bbox, int npose, float pad, float gs, int cap_n,
+                                  int cap_o, TargetGeom T, PoseGeom *__restrict__ out, int *__restrict__ totals) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < npose) {
+    PoseGeom G;
+    vt_grid sg;
+    bool ok = true;
+    for (int k = 0; k < 3; ++k) {
+      // oracle vo_sim_grid: pad the box, count voxels, snap the far end to the lattice
+      float mn = fkey_inv(bbox[p * 6 + k]), mx = fkey_inv(bbox[p * 6 + 3 + k]);
+      mn -= pad;
+      mx += pad;
+      float ax = mx - mn;
+      const int nv = (int)ceil((double)(ax / gs));
+      ax = (float)(nv - 1) * gs;
+      G.org[k] = mn;
+      G.nv[k] = nv;
+      if (nv < 2 || nv > cap_n) ok = false;
+      sg.origin[k] = (double)mn;
+      sg.xaxis[k] = sg.yaxis[k] = sg.zaxis[k] = 0.0;
+      if (k == 0) sg.xaxis[0] = (double)ax;
+      if (k == 1) sg.yaxis[1] = (double)ax;
+      if (k == 2) sg.zaxis[2] = (double)ax;
+    }
+    sg.xsize = G.nv[0]; sg.ysize = G.nv[1]; sg.zsize = G.nv[2];
+    G.tiles[0] = (G.nv[0] + kTX - 1) / kTX;
+    G.tiles[1] = (G.nv[1] + kTY - 1) / kTY;
+    G.tiles[2] = (G.nv[2] + kTZ - 1) / kTZ;
+    if (!ok) { G.tiles[0] = G.tiles[1] = G.tiles[2] = 0; }
+    G.valid = 0;
+    G.cc_items = 0; G.cc_xt = 0; G.cc_zc = 0;
+    for (int k = 0; k < 3; ++k) { G.no[k] = 0; G.oorg[k] = 0; G.od[k] = 0; G.sinv_d[k] = 0; G.sinv_t[k] = 0; }
+    if (ok && T.present) {
+      vt_grid og;
+      geom::intersection_grid(sg, T.grid, og);  // MDFF.C:132 (A = sim, B = target)
+      float xd[3], yd[3], zd[3], sinv[16];
+      geom::cell_axes(og, xd, yd, zd);
+      geom::grid_inverse(sg, false, sinv);
+      const bool aligned = xd[1] == 0.f && xd[2] == 0.f && yd[0] == 0.f && yd[2] == 0.f && zd[0] == 0.f && zd[1] == 0.f;
+      const bool sep = aligned && geom::diagonal_inverse(sinv) && geom::diagonal_inverse(T.inv);
+      G.no[0] = og.xsize; G.no[1] = og.ysize; G.no[2] = og.zsize;
+      const bool fits = og.xsize > 0 && og.ysize > 0 && og.zsize > 0 && og.xsize <= cap_o && og.ysize <= cap_o &&
+                        og.zsize <= cap_o;
+      if (sep && fits) {
+        G.valid = 1;
+        for (int k = 0; k < 3; ++k) { G.oorg[k] = og.origin[k]; G.sinv_d[k] = sinv[5 * k]; G.sinv_t[k] = sinv[12 + k]; }
+        G.od[0] = xd[0]; G.od[1] = yd[1]; G.od[2] = zd[2];
+        G.cc_xt = (og.xsize + 31) / 32;
+        G.cc_zc = (og.zsize + kZChunkFit - 1) / kZChunkFit;
+        G.cc_items = G.cc_xt * og.ysize * G.cc_zc;
+      }
+    }
+    out[p] = G;
+  }
+  // exclusive prefixes (npose <= a few thousand: one thread, after everyone has written)
+  __syncthreads();
+  if (gridDim.x == 1 && threadIdx.x == 0) {
+    int t = 0, c = 0;
+    for (int i = 0; i < npose; ++i) {
+      out[i].tile_base = t;
+      out[i].cc_base = c;
+      t += out[i].tiles[0] * out[i].tiles[1] * out[i].tiles[2];
+      c += out[i].cc_items;
+    }
+    totals[0] = t;
+    totals[1] = c;
+  }
+}
+
+__global__ void __launch_bounds__(128) pose_tables_kernel(const PoseGeom *__restrict__ geo, TargetGeom T, int cap_o,
+                                                          geom::AxisEntry *__restrict__ tab) {
+  const int p = blockIdx.x;
+  const PoseGeom &G = geo[p];
+  if (!G.valid) return;
+  const int nsrcA[3] = {G.nv[0], G.nv[1], G.nv[2]};
+  const int nsrcB[3] = {T.grid.xsize, T.grid.ysize, T.grid.zsize};
+  for (int t = threadIdx.x; t < 6 * cap_o; t += blockDim.x) {
+    const int which = t / cap_o, g = t - which * cap_o;
+    const int ax = which % 3;
+    if (g >= G.no[ax]) continue;
+    geom::AxisEntry e;
+    if (which < 3) e = geom::axis_entry(ax, g, G.oorg[ax], G.od[ax], G.sinv_d[ax], G.sinv_t[ax], nsrcA[ax]);
+    else e = geom::axis_entry(ax, g, G.oorg[ax], G.od[ax], T.inv[5 * ax], T.inv[12 + ax], nsrcB[ax]);
+    tab[((size_t)p * 6 + which) * cap_o + g] = e;
+  }
+}
+
+int batch_prepare(const AtomSet &as, PoseBatch &pb, int npose, const PrepPose *d_prep, const float com[3],
+                  int identity, const vt_grid *target) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  if (npose > pb.B) { set_error("batch_prepare: %d poses > %d slots", npose, pb.B); return 1; }
+  bbox_reset_kernel<<<(npose * 6 + 127) / 128, 128, 0, c.stream>>>(pb.d_bbox, npose);
+  VT_LAUNCHED();
+  int gx = (as.n + 255) / 256;
+  if (gx > 64) gx = 64;
+  transform_kernel<<<dim3(gx, npose), 256, 0, c.stream>>>(as.d_xyzr, as.d_group, as.n, as.ngroups, d_prep,
+                                                           make_float3(com[0], com[1], com[2]), identity, pb.d_tpos,
+                                                           pb.d_tgroup, pb.d_bbox);
+  VT_LAUNCHED();
+  TargetGeom T;
+  memset(&T, 0, sizeof(T));
+  if (target) {
+    T.grid = *target;
+    grid_inverse(*target, false, T.inv);
+    T.present = 1;
+  }
+  if (npose > 1024) { set_error("batch_prepare: at most 1024 poses per batch"); return 1; }
+  pose_setup_kernel<<<1, 1024, 0, c.stream>>>(pb.d_bbox, npose, as.pad, as.prm.gs, pb.cap_n, pb.cap_o, T, pb.d_geom,
+                                              pb.d_totals);
+  VT_LAUNCHED();
+  if (target) {
+    pose_tables_kernel<<<npose, 128, 0, c.stream>>>(pb.d_geom, T, pb.cap_o, pb.d_tab);
+    VT_LAUNCHED();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ splat
+__device__ __forceinline__ int find_pose(const PoseGeom *__restrict__ geo, int npose, int item, bool cc) {
+  int lo = 0, hi = npose - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    const int base = cc ? geo[mid].cc_base : geo[mid].tile_base;
+    if (base <= item) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256, 2) splat_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
+                                                       int npose, int natoms, int ngroups,
+                                                       const float4 *__restrict__ tpos_all,
+                                                       const float4 *__restrict__ tgroup_all,
+                                                       const float4 *__restrict__ cst, float gs, float invgs,
+                                                       float *__restrict__ grid_all, long cap_grid) {
+  __shared__ __align__(16) float s_rec[kChunk * kRec];
+  __shared__ int s_ids[kMaxIds];
+  __shared__ int s_cells[256];
+  __shared__ int s_wcnt[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wx = warp & 1, wy = (warp >> 1) & 1, wz = warp >> 2;
+  const int ly = wy * 8 + (lane & 7), lz = wz * 4 + (lane >> 3);
+  const int total = totals[0];
+
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int p = find_pose(geo, npose, item, false);
+    const PoseGeom &G = geo[p];
+    const int local = item - G.tile_base;
+    const int tx = local % G.tiles[0], ty = (local / G.tiles[0]) % G.tiles[1], tz = local / (G.tiles[0] * G.tiles[1]);
+    const int x0 = tx * kTX, y0 = ty * kTY, z0 = tz * kTZ;
+    const int nv0 = G.nv[0], nv1 = G.nv[1], nv2 = G.nv[2];
+    const float ox = G.org[0], oy = G.org[1], oz = G.org[2];
+    const float4 *__restrict__ tpos = tpos_all + (size_t)p * natoms;
+    const float4 *__restrict__ tgroup = tgroup_all + (size_t)p * ngroups;
+    // tile box in cartesian space with one voxel of slack for the integer truncations
+    const float bx0 = ox + (x0 - 1) * gs, bx1 = ox + (x0 + kTX) * gs;
+    const float by0 = oy + (y0 - 1) * gs, by1 = oy + (y0 + kTY) * gs;
+    const float bz0 = oz + (z0 - 1) * gs, bz1 = oz + (z0 + kTZ) * gs;
+
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+    int nids = 0;
+
+    // staged compute over s_ids[0..count)
+    auto flush = [&](int count) {
+      for (int c0 = 0; c0 < count; c0 += kChunk) {
+        const int cn = min(kChunk, count - c0);
+        // ---- stage: 4 threads per atom ----
+        {
+          const int slot = tid >> 2, sub = tid & 3;
+          if (slot < cn) {
+            const int id = s_ids[c0 + slot];
+            const float4 a4 = tpos[id];
+            const float4 k4 = cst[id];
+            const float ax = a4.x - ox, ay = a4.y - oy, az = a4.z - oz;  // xyzr = pos - origin
+            const float arinv = k4.x, rl = k4.z;
+            float t = ax * invgs;
+            const int xmin = max(__float2int_rz(t - rl), 0), xmax = min(__float2int_rz(t + rl), nv0 - 1);
+            t = ay * invgs;
+            const int ymin = max(__float2int_rz(t - rl), 0), ymax = min(__float2int_rz(t + rl), nv1 - 1);
+            t = az * invgs;
+            const int zmin = max(__float2int_rz(t - rl), 0), zmax = min(__float2int_rz(t + rl), nv2 - 1);
+            float *rec = s_rec + slot * kRec;
+            if (sub < 2) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int X = x0 + sub * 8 + k;
+                const float dx = (float)X * gs - ax;
+                const float e = ex2_approx((dx * dx) * arinv);
+                rec[sub * 8 + k] = (X >= xmin && X <= xmax) ? e : 0.0f;
+              }
+            } else if (sub == 2) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const int Y = y0 + k;
+                const float dy = (float)Y * gs - ay;
+                rec[16 + k] = (Y >= ymin && Y <= ymax) ? dy * dy : INFINITY;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int Z = z0 + k;
+                const float dz = (float)Z * gs - az;
+                rec[32 + k] = (Z >= zmin && Z <= zmax) ? dz * dz : INFINITY;
+              }
+              rec[40] = arinv;
+              rec[41] = k4.y;  // radlim^2
+              int mask = 0;
+#pragma unroll
+              for (int w = 0; w < 8; ++w) {
+                const int rx = x0 + (w & 1) * 8, ry = y0 + ((w >> 1) & 1) * 8, rz = z0 + (w >> 2) * 4;
+                const bool hit = xmin <= rx + 7 && xmax >= rx && ymin <= ry + 7 && ymax >= ry && zmin <= rz + 3 && zmax >= rz;
+                mask |= hit ? (1 << w) : 0;
+              }
+              rec[42] = __int_as_float(mask);
+            }
+          }
+        }
+        __syncthreads();
+        // ---- compute: each thread 8 x-voxels of one (y,z) ----
+        for (int a = 0; a < cn; ++a) {
+          const float *rec = s_rec + a * kRec;
+          const int mask = __float_as_int(rec[42]);
+          if (!((mask >> warp) & 1)) continue;               // warp-uniform
+          const float d2 = rec[16 + ly] + rec[32 + lz];      // dy*dy + dz*dz
+          const bool pass = d2 < rec[41];                    // !(dy2dz2 >= radlim2)
+          if (!__any_sync(0xffffffffu, pass)) continue;
+          const float e = pass ? ex2_approx(d2 * rec[40]) : 0.0f;
+          const float4 e0 = *reinterpret_cast<const float4 *>(rec + wx * 8);
+          const float4 e1 = *reinterpret_cast<const float4 *>(rec + wx * 8 + 4);
+          acc[0] = __fmaf_rn(e0.x, e, acc[0]); acc[1] = __fmaf_rn(e0.y, e, acc[1]);
+          acc[2] = __fmaf_rn(e0.z, e, acc[2]); acc[3] = __fmaf_rn(e0.w, e, acc[3]);
+          acc[4] = __fmaf_rn(e1.x, e, acc[4]); acc[5] = __fmaf_rn(e1.y, e, acc[5]);
+          acc[6] = __fmaf_rn(e1.z, e, acc[6]); acc[7] = __fmaf_rn(e1.w, e, acc[7]);
+        }
+        __syncthreads();
+      }
+    };
+
+    for (int g0 = 0; g0 < ngroups; g0 += 256) {
+      // ---- cull 256 groups: thread per group, sphere vs tile box ----
+      const int g = g0 + tid;
+      bool hit = false;
+      if (g < ngroups) {
+        const float4 c = tgroup[g];
+        const float dx = fmaxf(fmaxf(bx0 - c.x, 0.0f), c.x - bx1);
+        const float dy = fmaxf(fmaxf(by0 - c.y, 0.0f), c.y - by1);
+        const float dz = fmaxf(fmaxf(bz0 - c.z, 0.0f), c.z - bz1);
+        hit = dx * dx + dy * dy + dz * dz <= c.w * c.w;
+      }
+      const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) s_wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int off = 0, nc = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { const int cw = s_wcnt[w]; if (w < warp) off += cw; nc += cw; }
+      if (hit) s_cells[off + __popc(bal & ((1u << lane) - 1u))] = g;
+      __syncthreads();
+      // ---- exact atom test: warp per surviving group ----
+      for (int c0 = 0; c0 < nc; c0 += 8) {
+        bool take = false;
+        int id = -1;
+        if (c0 + warp < nc) {
+          id = s_cells[c0 + warp] * 32 + lane;
+          if (id < natoms) {
+            const float4 a4 = tpos[id];
+            const float rl = cst[id].z;
+            const float ax = a4.x - ox, ay = a4.y - oy, az = a4.z - oz;
+            float t = ax * invgs;
+            const int xmin = max(__float2int_rz(t - rl), 0), xmax = min(__float2int_rz(t + rl), nv0 - 1);
+            t = ay * invgs;
+            const int ymin = max(__float2int_rz(t - rl), 0), ymax = min(__float2int_rz(t + rl), nv1 - 1);
+            t = az * invgs;
+            const int zmin = max(__float2int_rz(t - rl), 0), zmax = min(__float2int_rz(t + rl), nv2 - 1);
+            take = xmin <= x0 + kTX - 1 && xmax >= x0 && ymin <= y0 + kTY - 1 && ymax >= y0 && zmin <= z0 + kTZ - 1 &&
+                   zmax >= z0 && xmin <= xmax && ymin <= ymax && zmin <= zmax;
+          }
+        }
+        const unsigned int b2 = __ballot_sync(0xffffffffu, take);
+        if (lane == 0) s_wcnt[warp] = __popc(b2);
+        __syncthreads();
+        int o2 = nids, add = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int cw = s_wcnt[w]; if (w < warp) o2 += cw; add += cw; }
+        if (take) s_ids[o2 + __popc(b2 & ((1u << lane) - 1u))] = id;
+        nids += add;
+        __syncthreads();
+        if (nids > kMaxIds - 256) { flush(nids); nids = 0; }
+      }
+    }
+    if (nids > 0) flush(nids);
+
+    // ---- every voxel of the tile written exactly once ----
+    const int Y = y0 + ly, Z = z0 + lz, X0 = x0 + wx * 8;
+    if (Y < nv1 && Z < nv2) {
+      float *row = grid_all + (size_t)p * cap_grid + ((size_t)Z * nv1 + Y) * nv0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (X0 + k < nv0) row[X0 + k] = acc[k];
+    }
+    __syncthreads();
+  }
+}
+
+int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  const int grid = c.sm_count * 2 * 4;  // persistent, dynamic enough for uneven tiles
+  splat_kernel<<<grid, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, as.ngroups, pb.d_tpos, pb.d_tgroup,
+                                           as.d_const, as.prm.gs, as.prm.invgs, pb.d_grid, pb.cap_grid);
+  VT_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ batched cc
+__global__ void __launch_bounds__(256) pose_cc_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
+                                                      int npose, const float *__restrict__ grid_all, long cap_grid,
+                                                      const float *__restrict__ tdata, int tnx, int tny,
+                                                      const geom::AxisEntry *__restrict__ tab_all, int cap_o,
+                                                      long cap_items, double thr, double *__restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int total = totals[1];
+  const int wstride = gridDim.x * 8;
+  const long planeB = (long)tnx * tny;
+  for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < total; item += wstride) {
+    const int p = find_pose(geo, npose, item, true);
+    const PoseGeom &G = geo[p];
+    const int local = item - G.cc_base;
+    const int xb = local % G.cc_xt;
+    const int r = local / G.cc_xt;
+    const int gy = r % G.no[1], zc = r / G.no[1];
+    const int gx = xb * 32 + lane;
+    const geom::AxisEntry *__restrict__ T = tab_all + (size_t)p * 6 * cap_o;
+    const float *__restrict__ A = grid_all + (size_t)p * cap_grid;
+    const int anx = G.nv[0];
+    const long planeA = (long)anx * G.nv[1];
+    float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;
+    int cnt = 0;
+    if (gx < G.no[0]) {
+      const geom::AxisEntry ax = T[gx], ay = T[cap_o + gy];
+      const geom::AxisEntry bx = T[3 * cap_o + gx], by = T[4 * cap_o + gy];
+      if (ax.inside && ay.inside && bx.inside && by.inside) {
+        const long a_row0 = (long)ay.i0 * anx, a_row1 = (long)ay.i1 * anx;
+        const long b_row0 = (long)by.i0 * tnx, b_row1 = (long)by.i1 * tnx;
+        PlaneCache pa, pb;
+        const int zend = min(G.no[2], (zc + 1) * kZChunkFit);
+        for (int gz = zc * kZChunkFit; gz < zend; ++gz) {
+          const geom::AxisEntry az = T[2 * cap_o + gz], bz = T[5 * cap_o + gz];
+          if (!az.inside || !bz.inside) continue;
+          const float vA = sep_sample(A, planeA, a_row0, a_row1, ax.i0, ax.i1, ax.f, ay.f, az, pa);
+          if (is_nan_bits(vA) || !((double)vA >= thr)) continue;
+          const float vB = sep_sample(tdata, planeB, b_row0, b_row1, bx.i0, bx.i1, bx.f, by.f, bz, pb);
+          if (is_nan_bits(vB)) continue;
+          fA += vA; fB += vB; fAA += vA * vA; fBB += vB * vB; fAB += vA * vB;
+          ++cnt;
+        }
+      }
+    }
+    double v[6] = {(double)fA, (double)fB, (double)fAA, (double)fBB, (double)fAB, (double)cnt};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+      double *o = part + ((size_t)p * cap_items + local) * 6;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) o[k] = v[k];
+    }
+  }
+}
+
+// one block per pose: ordered sum of the warp partials, then MDFF.C:143-149
+__global__ void __launch_bounds__(256) pose_cc_finish_kernel(const PoseGeom *__restrict__ geo,
+                                                             const double *__restrict__ part, long cap_items,
+                                                             float *__restrict__ cc_out, double *__restrict__ sums_out) {
+  __shared__ double sm[6 * 32];
+  const int p = blockIdx.x;
+  const PoseGeom &G = geo[p];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const double *src = part + (size_t)p * cap_items * 6;
+  for (int i = threadIdx.x; i < G.cc_items; i += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] += src[(size_t)i * 6 + k];
+  block_sum<6>(acc, sm);
+  if (threadIdx.x == 0) {
+    float cc = quiet_nan();
+    if (G.valid) {
+      const int size = (int)acc[5];
+      const double mA = acc[0] / size, mB = acc[1] / size;
+      const double sdA = sqrt(acc[2] / size - mA * mA);
+      const double sdB = sqrt(acc[3] / size - mB * mB);
+      const double c = (acc[4] - size * mA * mB) / (size * sdA * sdB);
+      cc = (float)c;  // calc_cc: float return_cc += cc (TclVoltool.C:75,126)
+    }
+    cc_out[p] = cc;
+    if (sums_out)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) sums_out[(size_t)p * 6 + k] = acc[k];
+  }
+}
+
+int batch_cc(PoseBatch &pb, int npose, const vt_map *target, double threshold, float *d_cc, double *d_sums) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  pose_cc_kernel<<<c.sm_count * 8, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, pb.d_grid, pb.cap_grid, target->d,
+                                                       target->grid.xsize, target->grid.ysize, pb.d_tab, pb.cap_o,
+                                                       pb.cap_items, threshold, pb.d_part);
+  VT_LAUNCHED();
+  pose_cc_finish_kernel<<<npose, 256, 0, c.stream>>>(pb.d_geom, pb.d_part, pb.cap_items, d_cc, d_sums);
+  VT_LAUNCHED();
+  return 0;
+}
+
+}  // namespace vt
