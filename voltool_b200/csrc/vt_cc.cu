@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) cc_sep_kernel(DevMap A, DevMap B, in
     const long a_row0 = (long)ay.i0 * A.nx, a_row1 = (long)ay.i1 * A.nx;
     const long b_row0 = (long)by.i0 * B.nx, b_row1 = (long)by.i1 * B.nx;
     PlaneCache pa, pb;
-    float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;  // f32 within a chunk of <= 16, then f64
+    double fA = 0.0, fB = 0.0, fAA = 0.0, fBB = 0.0, fAB = 0.0;  // MDFF.C:79-83: double sums of float terms
     int cnt = 0;
     const int zend = min(nz, (zc + 1) * kZChunk);
     for (int gz = zc * kZChunk; gz < zend; ++gz) {
@@ -155,10 +155,10 @@ __global__ void __launch_bounds__(kThreads) cc_sep_kernel(DevMap A, DevMap B, in
       if (is_nan_bits(vA) || !((double)vA >= thr)) continue;
       const float vB = sep_sample(B.d, planeB, b_row0, b_row1, bx.i0, bx.i1, bx.f, by.f, bz, pb);
       if (is_nan_bits(vB)) continue;
-      fA += vA; fB += vB; fAA += vA * vA; fBB += vB * vB; fAB += vA * vB;
+      fA += (double)vA; fB += (double)vB; fAA += (double)(vA * vA); fBB += (double)(vB * vB); fAB += (double)(vA * vB);
       ++cnt;
     }
-    acc[0] += (double)fA; acc[1] += (double)fB; acc[2] += (double)fAA; acc[3] += (double)fBB; acc[4] += (double)fAB;
+    acc[0] += fA; acc[1] += fB; acc[2] += fAA; acc[3] += fBB; acc[4] += fAB;
     acc[5] += (double)cnt;
   }
   block_sum<6>(acc, sm);
@@ -224,16 +224,16 @@ __global__ void __launch_bounds__(kThreads) binary_kernel(DevMap A, DevMap B, De
         const float vB = INTERP ? sample_interp<false>(B, x, y, z) : sample_nearest<false>(B, x, y, z);
         if (UNION) {
           const bool na = is_nan_bits(vA), nb = is_nan_bits(vB);
-          r = (!na && !nb) ? vA * vB : (!na ? vA : (!nb ? vB : 0.0f));
+          r = (!na && !nb) ? nan_like_x86(vA * vB, vA, vB) : (!na ? vA : (!nb ? vB : 0.0f));
         } else {
-          r = vA * vB;
+          r = nan_like_x86(vA * vB, vA, vB);
         }
       } else {  // zero outside, Voltool.C:249-300, 352-377
         const float vA = INTERP ? sample_interp<true>(A, x, y, z) : sample_nearest<true>(A, x, y, z);
         const float vB = INTERP ? sample_interp<true>(B, x, y, z) : sample_nearest<true>(B, x, y, z);
-        if (OP == VT_ADD) r = vA + vB;
-        else if (OP == VT_SUBTRACT) r = vA - vB;
-        else r = (float)((double)(vA + vB) * 0.5);
+        if (OP == VT_ADD) r = nan_like_x86(vA + vB, vA, vB);
+        else if (OP == VT_SUBTRACT) r = nan_like_x86(vA - vB, vA, vB);
+        else r = nan_like_x86((float)((double)(vA + vB) * 0.5), vA, vB);
       }
       out[row * C.nx + gx] = r;
     }

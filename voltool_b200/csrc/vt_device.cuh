@@ -75,6 +75,19 @@ __device__ __forceinline__ int trunc_like_x86(float v) {
 __device__ __forceinline__ bool is_nan_bits(float f) { return (__float_as_uint(f) << 1) > 0xff000000u; }
 __device__ __forceinline__ float quiet_nan() { return __uint_as_float(0x7fc00000u); }
 
+// x86 SSE scalar arithmetic hands back the first NaN operand (quieted), and 0xffc00000 when it has
+// to make one up (inf-inf, 0*inf, 0/0); CUDA returns the canonical 0x7fffffff for both.  Where
+// NaNs can legitimately flow through bit-exact ops this restores the reference's bits.  `a..d`
+// are the operands in the order the reference expression consults them.
+__device__ __forceinline__ float nan_like_x86(float r, float a, float b = 0.f, float c = 0.f, float d = 0.f) {
+  if (!is_nan_bits(r)) return r;
+  if (is_nan_bits(a)) return __uint_as_float(__float_as_uint(a) | 0x00400000u);
+  if (is_nan_bits(b)) return __uint_as_float(__float_as_uint(b) | 0x00400000u);
+  if (is_nan_bits(c)) return __uint_as_float(__float_as_uint(c) | 0x00400000u);
+  if (is_nan_bits(d)) return __uint_as_float(__float_as_uint(d) | 0x00400000u);
+  return __uint_as_float(0xffc00000u);
+}
+
 struct DevMap {  // lookup constants of one source map
   const float *__restrict__ d;
   float inv[16];
@@ -128,7 +141,15 @@ __device__ __forceinline__ float trilinear(const DevMap &m, float xv, float yv, 
   const float xe = d0 + xf * (d1 - d0);
   const float ya = xa + yf * (xb - xa);
   const float yb = xc + yf * (xe - xc);
-  return ya + zf * (yb - ya);
+  const float r = ya + zf * (yb - ya);
+  if (is_nan_bits(r)) {  // rare: NaN voxels or inf arithmetic; restore the x86 payload
+    const float v[8] = {a0, a1, b0, b1, c0, c1, d0, d1};
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (is_nan_bits(v[k])) return __uint_as_float(__float_as_uint(v[k]) | 0x00400000u);
+    return __uint_as_float(0xffc00000u);
+  }
+  return r;
 }
 
 // voxel_value_interpolate_from_coord[_safe], VolumetricData.C:305-322 / 338-355

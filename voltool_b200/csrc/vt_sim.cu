@@ -74,8 +74,10 @@ static void group_spheres(const AtomSet &as, const std::vector<float4> &xyzr, st
       const float dx = xyzr[i].x - c[0], dy = xyzr[i].y - c[1], dz = xyzr[i].z - c[2];
       r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
     }
-    // reach = sphere radius + largest cutoff + slack for float rounding of the rigid transform
-    const float reach = std::sqrt(r2) + maxcut + 0.05f + 1e-4f * (std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]));
+    // reach = sphere radius + the farthest voxel an atom touches + slack for float rounding of the
+    // rigid transform.  The footprint is a box in x and a disc in y-z (radius gausslim*sigma each),
+    // so its far corner sits sqrt(2) cutoffs from the atom.
+    const float reach = std::sqrt(r2) + 1.41422f * maxcut + 0.05f + 1e-4f * (std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]));
     groups[g] = make_float4(c[0], c[1], c[2], reach);
   }
 }
@@ -281,10 +283,9 @@ struct TargetGeom {
   int present;
 };
 
-__global__ void pose_setup_kernel(const unsigned int *__restrict__ bbox, int npose, float pad, float gs, int cap_n,
+__global__ void __launch_bounds__(256) pose_setup_kernel(const unsigned int *__restrict__ bbox, int npose, float pad, float gs, int cap_n,
                                   int cap_o, TargetGeom T, PoseGeom *__restrict__ out, int *__restrict__ totals) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < npose) {
+  for (int p = threadIdx.x; p < npose; p += blockDim.x) {
     PoseGeom G;
     vt_grid sg;
     bool ok = true;
@@ -337,7 +338,7 @@ __global__ void pose_setup_kernel(const unsigned int *__restrict__ bbox, int npo
   }
   // exclusive prefixes (npose <= a few thousand: one thread, after everyone has written)
   __syncthreads();
-  if (gridDim.x == 1 && threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
     int t = 0, c = 0;
     for (int i = 0; i < npose; ++i) {
       out[i].tile_base = t;
@@ -389,7 +390,7 @@ int batch_prepare(const AtomSet &as, PoseBatch &pb, int npose, const PrepPose *d
     T.present = 1;
   }
   if (npose > 1024) { set_error("batch_prepare: at most 1024 poses per batch"); return 1; }
-  pose_setup_kernel<<<1, 1024, 0, c.stream>>>(pb.d_bbox, npose, as.pad, as.prm.gs, pb.cap_n, pb.cap_o, T, pb.d_geom,
+  pose_setup_kernel<<<1, 256, 0, c.stream>>>(pb.d_bbox, npose, as.pad, as.prm.gs, pb.cap_n, pb.cap_o, T, pb.d_geom,
                                               pb.d_totals);
   VT_LAUNCHED();
   if (target) {
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(256) pose_cc_kernel(const PoseGeom *__restrict
     const float *__restrict__ A = grid_all + (size_t)p * cap_grid;
     const int anx = G.nv[0];
     const long planeA = (long)anx * G.nv[1];
-    float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;
+    double fA = 0.0, fB = 0.0, fAA = 0.0, fBB = 0.0, fAB = 0.0;  // MDFF.C:79-83: double sums of float terms
     int cnt = 0;
     if (gx < G.no[0]) {
       const geom::AxisEntry ax = T[gx], ay = T[cap_o + gy];
@@ -635,12 +636,12 @@ __global__ void __launch_bounds__(256) pose_cc_kernel(const PoseGeom *__restrict
           if (is_nan_bits(vA) || !((double)vA >= thr)) continue;
           const float vB = sep_sample(tdata, planeB, b_row0, b_row1, bx.i0, bx.i1, bx.f, by.f, bz, pb);
           if (is_nan_bits(vB)) continue;
-          fA += vA; fB += vB; fAA += vA * vA; fBB += vB * vB; fAB += vA * vB;
+          fA += (double)vA; fB += (double)vB; fAA += (double)(vA * vA); fBB += (double)(vB * vB); fAB += (double)(vA * vB);
           ++cnt;
         }
       }
     }
-    double v[6] = {(double)fA, (double)fB, (double)fAA, (double)fBB, (double)fAB, (double)cnt};
+    double v[6] = {fA, fB, fAA, fBB, fAB, (double)cnt};
 #pragma unroll
     for (int k = 0; k < 6; ++k) v[k] = warp_sum(v[k]);
     if (lane == 0) {

@@ -156,16 +156,16 @@ __device__ __forceinline__ float unary_apply(float x, const UnaryParams &p) {
   switch (OP) {
     case U_CLAMP:  // VolumetricData.C:637-638 (else-if: NaN passes through)
       return x < p.p0 ? p.p0 : (x > p.p1 ? p.p1 : x);
-    case U_SCALE: return x * p.p0;                       // :659
-    case U_ADD: return x + p.p0;                         // :683
-    case U_RESCALE: return p.p0 + p.p1 * (x - p.p2);     // :706  min + ratio*(x - oldmin)
-    case U_SIGMA: return (x - p.p0) * p.p1;              // :944-945  (x -= mean; x *= 1/sigma)
+    case U_SCALE: return nan_like_x86(x * p.p0, x, p.p0);                       // :659
+    case U_ADD: return nan_like_x86(x + p.p0, x, p.p0);                         // :683
+    case U_RESCALE: return nan_like_x86(p.p0 + p.p1 * (x - p.p2), p.p0, p.p1, x, p.p2);  // :706  min + ratio*(x - oldmin)
+    case U_SIGMA: return nan_like_x86((x - p.p0) * p.p1, x, p.p0, p.p1);              // :944-945  (x -= mean; x *= 1/sigma)
     case U_BINMASK: return x > p.p0 ? 1.0f : 0.0f;       // :960
     case U_MDFFPOT: {                                    // :1010-1016
       float v = x;
       if ((double)v < p.pd) v = (float)p.pd;
       v = v * -1.0f;
-      return p.p0 * (v - p.p1);                          // ratio * (v - mininvert)
+      return nan_like_x86(p.p0 * (v - p.p1), p.p0, v, p.p1);  // ratio * (v - mininvert)
     }
   }
   return x;
