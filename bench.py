@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py -- voltool fit pose-evaluation throughput on B200 (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (torchrun for N > 1)
+  python bench.py --impl reference --gpus N ...             the reference's CPU path on the host cores
+
+One step = one batch of rigid poses (rotation x translation candidates of the cfg2 grid search)
+evaluated for a 50k-atom structure against a resident 256^3 target map: transform -> Gaussian
+splat on the pose's own grid -> thresholded CC (threshold 0.1) -> per-shard best.  Each rank
+evaluates its own slice of the pose list (weak scaling, no data-path collective); the per-shard
+best (cc, pose index) is merged with one small all_gather per step.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each field means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PLANTED = (58.0, 29.0, 315.0)     # 48/24/312 on the 24-degree lattice + 8/4/0 + 2/1/3 refinements
+RESOLUTION = 5.0
+FLOP_PER_PAIR = 7.0               # 1 exp + ~6 FP32 flops per (atom, voxel) pair in the cutoff box
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pose_list():
+    """10 000 rotations (25 x 20 x 20 Euler lattice) x 27 translations (+-1 voxel) = 270 000 poses"""
+    rx = np.arange(25) * (360.0 / 25)
+    ry = np.arange(20) * (360.0 / 20)
+    rz = np.arange(20) * (360.0 / 20)
+    rot = np.stack(np.meshgrid(rx, ry, rz, indexing="ij"), -1).reshape(-1, 3)
+    sh = np.stack(np.meshgrid([-1.0, 0.0, 1.0], [-1.0, 0.0, 1.0], [-1.0, 0.0, 1.0], indexing="ij"), -1).reshape(-1, 3)
+    poses = np.concatenate([np.repeat(rot, len(sh), 0), np.tile(sh, (len(rot), 1))], 1).astype(np.float32)
+    # interleave so that every slice mixes rotations (pose cost varies with the rotated bounding box)
+    perm = np.random.default_rng(2003).permutation(len(poses))
+    return np.ascontiguousarray(poses[perm])
+
+
+def splat_pairs(radii, radscale, gspacing, gausslim=4.0):
+    """algorithmic (atom, voxel) pairs of one splat: sum over atoms of prod over axes (2*floor(cutoff/gs)+1)"""
+    b = 2 * np.floor(gausslim * radii.astype(np.float64) * radscale / gspacing) + 1
+    return float(np.sum(b ** 3))
+
+
+# ================================================================================================ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import voltool_b200 as vt
+    from voltool_b200.synth import make_structure, add_noise
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    vt.init(local)
+    props = vt.device_props()
+    stream = torch.cuda.ExternalStream(vt.lib().vt_stream(), device=torch.device("cuda", local))
+    peaks = load_peaks()
+
+    # ---- workload (every rank holds the full target map and atom set) ----
+    n = args.map
+    pos, radii, mass = make_structure(args.atoms, 52.0 * (args.atoms / 50000.0) ** (1 / 3), seed=2001,
+                                      center=(0.5 * (n - 1),) * 3)
+    com0 = vt.measure_center(pos, mass)
+    planted = vt.pose_apply(pos, com0, PLANTED)
+    radscale, gsp, quality = vt.sim_policy(RESOLUTION)
+    tmap = vt.sim(planted, radii, quality, radscale, 1.0)      # 1 A sampling of the planted pose
+    g = tmap.grid
+    padm = [(n - s) // 2 for s in (g.xsize, g.ysize, g.zsize)]
+    padp = [n - s - m for s, m in zip((g.xsize, g.ysize, g.zsize), padm)]
+    tmap.pad(padm[0], padp[0], padm[1], padp[1], padm[2], padp[2])
+    tmap.upload(add_noise(tmap.data, 0.02, seed=2002))
+    tg = tmap.grid
+    assert (tg.xsize, tg.ysize, tg.zsize) == (n, n, n)
+    dencom = tmap.vol_com()
+    pos = (pos + (dencom - com0)[None, :]).astype(np.float32)   # fit's COM alignment (TclVoltool.C:800)
+    com = vt.measure_center(pos, mass)
+    ctx = vt.FitContext(pos, radii, tmap, RESOLUTION)
+
+    poses = pose_list()
+    P = args.poses
+    W, K = args.warmup, args.steps
+
+    def slice_for(step):
+        base = ((step * world + rank) * P) % len(poses)
+        idx = (base + np.arange(P)) % len(poses)
+        return poses[idx]
+
+    d_cc = torch.empty(P, dtype=torch.float32, device="cuda")
+    best_local = torch.empty(2, dtype=torch.float32, device="cuda")
+    gathered = torch.empty(2 * world, dtype=torch.float32, device="cuda")
+    dev_poses = [torch.from_numpy(slice_for(s)).cuda() for s in range(W + K)]
+    torch.cuda.synchronize()
+
+    def step_resident(s):
+        ctx.eval_poses_device(com, dev_poses[s].data_ptr(), P, d_cc.data_ptr())
+        with torch.cuda.stream(stream):
+            v, i = torch.max(torch.nan_to_num(d_cc, nan=-2.0), 0)
+            best_local[0], best_local[1] = v, i.to(torch.float32)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, best_local)   # the one collective of the path
+            else:
+                gathered.copy_(best_local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, first, count):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+        for s in range(first, first + count):
+            fn(s)
+        with torch.cuda.stream(stream):
+            e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for s in range(W):
+        step_resident(s)
+    launches0 = vt.launch_count()
+    vt.profile_reset()
+    vt.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, W, K)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = vt.launch_count() - launches0 + 2 * K   # + torch max / copy per step
+    prof = {k: vt.profile_get(k) for k in ("transform", "splat", "pose_cc")}
+    vt.profile_enable(False)
+    value = world * P * K / (ms_total * 1e-3)
+    best = gathered.cpu().numpy().reshape(world, 2)
+
+    # ---- e2e: the C-ABI call with HOST buffers (coordinates + pose list in, cc table out) ----
+    host_slices = [slice_for(s) for s in range(W + K)]
+    pinned = torch.from_numpy(pos.copy()).pin_memory()
+
+    def step_e2e(s):
+        ctx.set_origin(pinned.numpy())                       # H2D: 3*natoms floats (+ group spheres)
+        cc = ctx.eval_poses(com, host_slices[s])             # H2D: pose list; D2H: cc per pose
+        i = int(np.nanargmax(cc))
+        mine = torch.tensor([float(cc[i]), float(i)], device="cuda")
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, mine)
+        else:
+            gathered.copy_(mine)
+        return float(gathered[0].item())                     # D2H read of the merged result
+
+    step_e2e(0)
+    t0 = time.perf_counter()
+    ms_e2e = timed(step_e2e, W, K)
+    wall_e2e = time.perf_counter() - t0
+    e2e_value = world * P * K / (ms_e2e * 1e-3)
+    h2d = args.atoms * 16 + (args.atoms + 31) // 32 * 16 + P * 36
+    d2h = P * 4 + 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (splat): FP32/SFU bound, not HBM ----
+    pairs = splat_pairs(radii, radscale, gsp)
+    splat_ms, splat_n = prof["splat"]
+    poses_done = P * K
+    fp32_peak = props["sm_count"] * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    achieved = FLOP_PER_PAIR * pairs * poses_done / (splat_ms * 1e-3) / 1e12 if splat_ms > 0 else None
+    roofline = {"kernel": "splat_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": (achieved / fp32_peak) if achieved else None, "traffic": None,
+                "peak_source": f"{props['sm_count']} SMs x 128 lanes x 2 x sm_max_mhz ({peaks['source']} MEASURED_PEAKS); "
+                               "no tensor cores: nothing here is a contraction",
+                "pairs_per_pose": pairs, "flop_per_pair": FLOP_PER_PAIR,
+                "ms_per_launch": splat_ms / max(splat_n, 1), "launches": splat_n,
+                "share_of_step": {k: v[0] / ms_total for k, v in prof.items()}}
+
+    out = {"metric": "fit_poses_per_sec", "value": value, "unit": "poses/s", "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "cfg2 fit: 50k atoms into a 256^3 map, rotation x translation grid search",
+                      "atoms": args.atoms, "map": [n, n, n], "resolution": RESOLUTION, "poses_per_step_per_gpu": P,
+                      "pose_list": "25x20x20 Euler lattice x 3x3x3 shifts (270000), permuted, sliced per rank",
+                      "l2": "per-step working set (target 64 MiB + per-pose grids/coordinates, several GB) exceeds the 126 MB L2",
+                      "parallelism": f"pose-shard x{world}, one all_gather of (cc, index) per step"},
+           "clocks": clocks,
+           "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": ms_e2e / K, "wall_s": wall_e2e},
+           "gpu_launches": int(launches), "roofline": roofline,
+           "best_of_last_step": {"cc": float(best[:, 0].max()), "planted_deg": PLANTED}}
+
+    if world == 1:
+        out["cpu_baseline"] = cpu_baseline(pos, radii, com, tmap, poses, budget_s=args.cpu_budget)
+        if not args.no_extras:
+            out["ops"] = extra_ops(vt, peaks, args)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_ops(vt, peaks, args):
+    """the other BASELINE metrics on one GPU: correlate / smooth as HBM GB/s, sim+cc as voxels/s"""
+    import torch
+    res = {}
+    n = args.ops_map
+    g = vt.Grid.make((0, 0, 0), (n, n, n), 1.0)
+    rng = np.random.default_rng(4001)
+    a = rng.random(g.n, dtype=np.float32)
+    b = (0.7 * a + 0.3 * rng.random(g.n, dtype=np.float32)).astype(np.float32)
+    A, B = vt.VolMap(g, a), vt.VolMap(g, b)
+
+    def timeit(key, fn, reps=5):
+        fn()
+        vt.profile_reset(); vt.profile_enable(True)
+        for _ in range(reps):
+            fn()
+        ms, cnt = vt.profile_get(key)
+        vt.profile_enable(False)
+        return ms / reps
+
+    ms = timeit("cc", lambda: vt.cc_threaded(A, B))
+    gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
+    res["correlate"] = {"map": [n, n, n], "ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8,
+                        "cc": vt.cc_threaded(A, B)}
+    ms = timeit("unary", lambda: A.scalar_add(0.0))
+    gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
+    res["sadd"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8}
+    ms = timeit("stats", lambda: (A.scalar_add(0.0), A.sigma()))   # sadd invalidates mean+sigma -> 2 passes
+    res["sigma"] = {"ms": ms, "GB/s": 8.0 * g.n / (ms * 1e-3) / 1e9, "bytes_per_voxel": 8, "note": "mean pass + sigma pass"}
+    C = A.clone()
+    ms = timeit("blur", lambda: C.gaussian_blur(2.0), reps=3)
+    gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
+    res["smooth_sigma2"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8,
+                            "note": "3 separable passes move 24 B/voxel"}
+    del A, B, C
+    # cfg1: sim + cc, 10k atoms, res 5, 1 A spacing
+    from voltool_b200.synth import make_structure
+    pos, radii, _ = make_structure(10000, 30.0, seed=1001)
+    radscale, _, quality = vt.sim_policy(5.0, 1.0)
+    S = vt.sim(pos, radii, quality, radscale, 1.0)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        cc = vt.sim_cc(pos, radii, 5.0, S, gspacing=1.0)
+    vt.sync()
+    dt = (time.perf_counter() - t0) / reps
+    res["sim_cc_cfg1"] = {"voxels": S.gridsize(), "s_per_call": dt, "voxels_per_s": S.gridsize() / dt, "cc": cc,
+                          "note": "host call incl. atom sort/upload"}
+    return res
+
+
+# ================================================================================================ reference arm
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def load_reference():
+    """oracle/_ref (the reference's own object code) when present, else the C port"""
+    from oracle import pyoracle
+    if pyoracle.ref_available():
+        return pyoracle.Ref(), "reference"
+    return pyoracle.Oracle(), "port"
+
+
+def cpu_eval_poses(lib, kind, pos, radii, com, g, t, tvol, poses, threads):
+    """calc_cc per pose on the host cores: restated splat (OpenMP) + cc_threaded"""
+    if kind == "reference":
+        lib.set_numprocs(threads)
+        lib.install_cc_backend(tvol)
+    out = []
+    for q in poses:
+        p = pose_host(lib, pos, com, q)
+        out.append(lib.calc_cc(p, radii, g, t, RESOLUTION, nthreads=threads))
+    return out
+
+
+def pose_host(lib, pos, com, q):
+    """rigid pose in plain numpy float32 (rotate about com by X, Y, Z Euler degrees, then shift)"""
+    p = (pos - com[None, :]).astype(np.float32)
+    for ax, deg in enumerate(q[:3]):
+        a = np.float32(np.deg2rad(float(deg)))
+        c, s = np.float32(np.cos(float(a))), np.float32(np.sin(float(a)))
+        i, j = [(1, 2), (2, 0), (0, 1)][ax]
+        pi, pj = p[:, i].copy(), p[:, j].copy()
+        p[:, i] = pi * c - pj * s
+        p[:, j] = pi * s + pj * c
+    return (p + com[None, :] + np.asarray(q[3:6], np.float32)[None, :]).astype(np.float32)
+
+
+def cpu_baseline(pos, radii, com, tmap, poses, budget_s=20.0):
+    """rank 0, N=1: the reference CPU path timed on a bounded sample of the same pose list"""
+    from oracle.pyoracle import Grid as OGrid
+    lib, kind = load_reference()
+    g = OGrid()
+    tg = tmap.grid
+    for k in range(3):
+        g.origin[k], g.xaxis[k], g.yaxis[k], g.zaxis[k] = tg.origin[k], tg.xaxis[k], tg.yaxis[k], tg.zaxis[k]
+    g.xsize, g.ysize, g.zsize = tg.xsize, tg.ysize, tg.zsize
+    t = tmap.data
+    threads = cpu_threads()
+    tvol = lib.vol(g, t) if kind == "reference" else None
+    done, t0 = 0, time.perf_counter()
+    ccs = []
+    while done < 64:
+        ccs += cpu_eval_poses(lib, kind, pos, radii, com, g, t, tvol, poses[done:done + 2], threads)
+        done += 2
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    if kind == "reference":
+        lib.install_cc_backend(None)
+    return {"value": done / dt, "unit": "poses/s", "cores": threads, "kind": kind,
+            "sample": f"{done} poses of the same list, {dt:.1f} s; splat = documented restatement (QuickSurf not in the "
+                      f"snapshot, OpenMP z-slabs), cc = {'the reference cc_threaded object code' if kind == 'reference' else 'C port of cc_threaded'}",
+            "cc_first": float(ccs[0])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle.pyoracle import Grid as OGrid  # noqa: F401
+    from voltool_b200.synth import make_structure, add_noise
+    lib, kind = load_reference()
+    threads = cpu_threads()
+    n = args.map
+    pos, radii, mass = make_structure(args.atoms, 52.0 * (args.atoms / 50000.0) ** (1 / 3), seed=2001,
+                                      center=(0.5 * (n - 1),) * 3)
+    com0 = lib.measure_center(pos, mass)
+    planted = pose_host(lib, pos, com0, np.array(PLANTED + (0.0, 0.0, 0.0), np.float32))
+    radscale, gsp, quality = lib.sim_policy(RESOLUTION)
+    g, d = lib.sim(planted, radii, quality, radscale, 1.0, nthreads=threads)
+    padm = [(n - s) // 2 for s in (g.xsize, g.ysize, g.zsize)]
+    padp = [n - s - m for s, m in zip((g.xsize, g.ysize, g.zsize), padm)]
+    g, d = lib.pad(g, d, (padm[0], padp[0], padm[1], padp[1], padm[2], padp[2]))
+    d = add_noise(d, 0.02, seed=2002)
+    dencom = lib.vol_com(g, d)
+    pos = (pos + (dencom - com0)[None, :]).astype(np.float32)
+    com = lib.measure_center(pos, mass)
+    tvol = lib.vol(g, d) if kind == "reference" else None
+    poses = pose_list()
+    S = args.ref_poses
+    W, K = args.warmup, args.steps
+
+    def step(s):
+        sl = poses[(s * S) % len(poses):][:S]
+        return cpu_eval_poses(lib, kind, pos, radii, com, g, d, tvol, sl, threads)
+
+    for s in range(W):
+        step(s)
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        cc = step(s)
+    dt = time.perf_counter() - t0
+    value = S * K / dt
+    out = {"impl": "reference", "metric": "fit_poses_per_sec", "value": value, "unit": "poses/s", "n_gpus": args.gpus,
+           "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "cfg2 fit: 50k atoms into a 256^3 map, rotation x translation grid search",
+                      "atoms": args.atoms, "map": [n, n, n], "resolution": RESOLUTION, "poses_per_step": S,
+                      "note": "bounded sample of the same pose list; CPU only, rank 0"},
+           "cpu_baseline": {"value": value, "unit": "poses/s", "cores": threads, "kind": kind,
+                            "sample": f"{S} poses per step; splat = documented restatement (OpenMP), "
+                                      f"cc = {'reference cc_threaded object code (oracle/_ref)' if kind == 'reference' else 'C port'}"},
+           "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "last_cc": float(cc[-1])}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--atoms", type=int, default=50000)
+    ap.add_argument("--map", type=int, default=256)
+    ap.add_argument("--poses", type=int, default=2048, help="poses per step per GPU")
+    ap.add_argument("--ref-poses", type=int, default=4, help="poses per step of the CPU reference arm")
+    ap.add_argument("--ops-map", type=int, default=512, help="edge of the maps used by the extra ops legs")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

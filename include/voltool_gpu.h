@@ -54,6 +54,12 @@ const char *vt_last_error(void);
 int vt_device_props(int *sm_count, int *clock_khz, size_t *mem_bytes, char *name, int name_len);
 /* number of kernels this library has launched since vt_init (bench.py's gpu_launches) */
 long vt_launch_count(void);
+/* optional CUDA-event timing of the library's own kernels on its stream, by kernel class:
+   "transform" "setup" "splat" "pose_cc" "pose_finish" "cc" "stats" "unary" "binary" "blur" "resample".
+   vt_profile_get synchronises and returns the summed duration (ms) and the number of launches. */
+int vt_profile_enable(int on);
+int vt_profile_reset(void);
+int vt_profile_get(const char *kernel_class, double *ms_total, long *count);
 /* all library work runs on one stream; torch callers use this to order their own events */
 void *vt_stream(void);
 

@@ -107,6 +107,8 @@ def lib():
     L.vt_init.argtypes = [C.c_int]
     L.vt_launch_count.restype = C.c_long
     L.vt_stream.restype = C.c_void_p
+    L.vt_profile_enable.argtypes = [C.c_int]
+    L.vt_profile_get.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_long)]
     L.vt_device_props.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.c_char_p, C.c_int]
     L.vt_map_create.argtypes = [G, C.c_void_p, C.POINTER(M)]
     L.vt_map_create_from_device.argtypes = [G, C.c_void_p, C.POINTER(M)]
@@ -203,6 +205,21 @@ def device_props():
     name = C.create_string_buffer(128)
     _check(lib().vt_device_props(C.byref(sm), C.byref(khz), C.byref(mem), name, 128), "vt_device_props")
     return {"sm_count": sm.value, "clock_khz": khz.value, "mem_bytes": mem.value, "name": name.value.decode()}
+
+
+def profile_enable(on=True):
+    lib().vt_profile_enable(int(on))
+
+
+def profile_reset():
+    lib().vt_profile_reset()
+
+
+def profile_get(kernel_class):
+    """(total ms, launches) of one kernel class since the last reset (CUDA events on the library stream)"""
+    ms, n = C.c_double(), C.c_long()
+    _check(lib().vt_profile_get(kernel_class.encode(), C.byref(ms), C.byref(n)), "vt_profile_get")
+    return ms.value, n.value
 
 
 def f32(a):

@@ -83,12 +83,14 @@ int k_blur(const float *src, float *dst, float *tmp, int nx, int ny, int nz, con
   int grid = (int)(rows < (long)c.sm_count * 8 ? rows : (long)c.sm_count * 8);
   if (grid < 1) grid = 1;
   // x: src -> dst ; y: dst -> tmp ; z: tmp -> dst
+  prof_begin(PK_BLUR);
   blur_x_kernel<<<grid, 256, sizeof(float) * (nx + 2 * R), c.stream>>>(src, dst, nx, rows, R);
   VT_LAUNCHED();
   const int g2 = c.sm_count * 8;
   blur_axis_kernel<8><<<g2, 256, 0, c.stream>>>(dst, tmp, ny, (long)nx, (long)nx, (long)nz, R);
   VT_LAUNCHED();
   blur_axis_kernel<8><<<g2, 256, 0, c.stream>>>(tmp, dst, nz, (long)nx * ny, (long)nx * ny, 1L, R);
+  prof_end(PK_BLUR);
   VT_LAUNCHED();
   return 0;
 }

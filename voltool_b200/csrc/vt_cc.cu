@@ -192,14 +192,18 @@ int k_cc(const vt_map *A, const vt_map *B, double thr, double sums[5], long *n) 
     const long work = (long)((og.xsize + 31) / 32) * og.ysize * ((og.zsize + kZChunk - 1) / kZChunk);
     const long wblocks = (work + kThreads / 32 - 1) / (kThreads / 32);
     int grid = (int)(wblocks < (long)c.sm_count * 8 ? wblocks : (long)c.sm_count * 8);
+    prof_begin(PK_CC);
     cc_sep_kernel<<<grid, kThreads, 0, c.stream>>>(dA, dB, og.xsize, og.ysize, og.zsize, T.d, T.offAx, T.offAy, T.offAz,
                                                    T.offBx, T.offBy, T.offBz, thr, partials, c.d_ticket, dout);
+    prof_end(PK_CC);
     VT_LAUNCHED();
     dev_free(T.d);
   } else {
     const long rows = (long)og.ysize * og.zsize;
     int grid = (int)(rows < (long)c.sm_count * 8 ? rows : (long)c.sm_count * 8);
+    prof_begin(PK_CC);
     cc_generic_kernel<<<grid, kThreads, 0, c.stream>>>(dA, dB, dC, thr, partials, c.d_ticket, dout);
+    prof_end(PK_CC);
     VT_LAUNCHED();
   }
   VT_CUDA(cudaMemcpyAsync(c.h_pinned, dout, 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -263,6 +267,7 @@ int k_binary(int op, int interp, int use_union, const vt_map *A, const vt_map *B
   const long rows = (long)og.ysize * og.zsize;
   if (rows <= 0 || og.xsize <= 0) return 0;
   int grid = (int)(rows < (long)ctx().sm_count * 8 ? rows : (long)ctx().sm_count * 8);
+  prof_begin(PK_BINARY);
   switch (op) {
     case VT_ADD: launch_binary<VT_ADD>(interp, use_union, grid, dA, dB, dC, out); break;
     case VT_SUBTRACT: launch_binary<VT_SUBTRACT>(interp, use_union, grid, dA, dB, dC, out); break;
@@ -270,6 +275,7 @@ int k_binary(int op, int interp, int use_union, const vt_map *A, const vt_map *B
     case VT_AVERAGE: launch_binary<VT_AVERAGE>(interp, use_union, grid, dA, dB, dC, out); break;
     default: set_error("vt_binary: unknown op %d", op); return 1;
   }
+  prof_end(PK_BINARY);
   VT_LAUNCHED();
   return 0;
 }

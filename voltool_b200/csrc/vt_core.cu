@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "vt_device.cuh"
 
@@ -25,6 +26,36 @@ void set_error(const char *fmt, ...) {
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
   return 2;
+}
+
+// ---- per-kernel event timing -----------------------------------------------------------------
+struct ProfSpan { cudaEvent_t a, b; int key; bool closed; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+static const char *kProfNames[PK_COUNT] = {"transform", "setup", "splat", "pose_cc", "pose_finish", "cc", "stats",
+                                           "unary", "binary", "blur", "resample"};
+
+static cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(int key) {
+  if (!g_prof_on) return;
+  ProfSpan s{take_event(), take_event(), key, false};
+  cudaEventRecord(s.a, g_ctx.stream);
+  g_spans.push_back(s);
+}
+void prof_end(int key) {
+  if (!g_prof_on) return;
+  for (size_t i = g_spans.size(); i-- > 0;)
+    if (g_spans[i].key == key && !g_spans[i].closed) {
+      cudaEventRecord(g_spans[i].b, g_ctx.stream);
+      g_spans[i].closed = true;
+      return;
+    }
 }
 
 int dev_alloc(void **p, size_t bytes) {
@@ -204,5 +235,35 @@ int vt_map_upload(vt_map *m, const float *host) {
 }
 
 void vt_free_host(void *p) { free(p); }
+
+int vt_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+int vt_profile_reset(void) {
+  for (auto &s : g_spans) { g_event_pool.push_back(s.a); g_event_pool.push_back(s.b); }
+  g_spans.clear();
+  return 0;
+}
+int vt_profile_get(const char *name, double *ms_total, long *count) {
+  VT_REQUIRE_CTX();
+  VT_CUDA(cudaStreamSynchronize(ctx().stream));
+  int key = -1;
+  for (int k = 0; k < PK_COUNT; ++k)
+    if (!strcmp(name, kProfNames[k])) key = k;
+  if (key < 0) { set_error("vt_profile_get: unknown kernel class %s", name); return 1; }
+  double total = 0.0;
+  long n = 0;
+  for (auto &s : g_spans) {
+    if (s.key != key || !s.closed) continue;
+    float ms = 0.f;
+    VT_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+    total += ms;
+    ++n;
+  }
+  if (ms_total) *ms_total = total;
+  if (count) *count = n;
+  return 0;
+}
 
 }  // extern "C"

@@ -49,6 +49,12 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     }                                                                       \
   } while (0)
 
+// optional per-kernel CUDA-event timing on the library stream (bench.py's roofline leg)
+enum ProfKey { PK_TRANSFORM = 0, PK_SETUP, PK_SPLAT, PK_POSE_CC, PK_POSE_FINISH, PK_CC, PK_STATS, PK_UNARY, PK_BINARY,
+               PK_BLUR, PK_RESAMPLE, PK_COUNT };
+void prof_begin(int key);
+void prof_end(int key);
+
 int dev_alloc(void **p, size_t bytes);
 int dev_free(void *p);
 

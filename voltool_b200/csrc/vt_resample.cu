@@ -78,10 +78,12 @@ int k_downsample(const float *src, int ox, int oy, int oz, float *dst) {
   long rows = (long)ny * nz;
   if (rows < 1 || nx < 1) return 0;
   int grid = (int)(rows < (long)ctx().sm_count * 16 ? rows : (long)ctx().sm_count * 16);
+  prof_begin(PK_RESAMPLE);
   if ((ox & 1) == 0)
     downsample_kernel<<<grid, kThreads, 0, ctx().stream>>>(src, ox, oy, dst, nx, ny, nz);
   else
     downsample_kernel_scalar<<<grid, kThreads, 0, ctx().stream>>>(src, ox, oy, dst, nx, ny, nz);
+  prof_end(PK_RESAMPLE);
   VT_LAUNCHED();
   return 0;
 }
@@ -153,9 +155,11 @@ int k_supersample(const float *src, int ox, int oy, int oz, float *dst) {
   const int nx = 2 * ox - 1, ny = 2 * oy - 1;
   long rows = (long)ny * oz;
   int grid = (int)(rows < (long)ctx().sm_count * 16 ? rows : (long)ctx().sm_count * 16);
+  prof_begin(PK_RESAMPLE);
   supersample_xy_kernel<<<grid, kThreads, 0, ctx().stream>>>(src, ox, oy, oz, dst, nx, ny);
   VT_LAUNCHED();
   supersample_z_kernel<<<ctx().sm_count * 8, kThreads, 0, ctx().stream>>>(dst, nx, ny, oz);
+  prof_end(PK_RESAMPLE);
   VT_LAUNCHED();
   return 0;
 }

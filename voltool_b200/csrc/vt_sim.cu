@@ -378,9 +378,11 @@ int batch_prepare(const AtomSet &as, PoseBatch &pb, int npose, const PrepPose *d
   VT_LAUNCHED();
   int gx = (as.n + 255) / 256;
   if (gx > 64) gx = 64;
+  prof_begin(PK_TRANSFORM);
   transform_kernel<<<dim3(gx, npose), 256, 0, c.stream>>>(as.d_xyzr, as.d_group, as.n, as.ngroups, d_prep,
                                                            make_float3(com[0], com[1], com[2]), identity, pb.d_tpos,
                                                            pb.d_tgroup, pb.d_bbox);
+  prof_end(PK_TRANSFORM);
   VT_LAUNCHED();
   TargetGeom T;
   memset(&T, 0, sizeof(T));
@@ -591,8 +593,10 @@ int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
   const int grid = c.sm_count * 2 * 4;  // persistent, dynamic enough for uneven tiles
+  prof_begin(PK_SPLAT);
   splat_kernel<<<grid, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, as.ngroups, pb.d_tpos, pb.d_tgroup,
                                            as.d_const, as.prm.gs, as.prm.invgs, pb.d_grid, pb.cap_grid);
+  prof_end(PK_SPLAT);
   VT_LAUNCHED();
   return 0;
 }
@@ -685,9 +689,11 @@ __global__ void __launch_bounds__(256) pose_cc_finish_kernel(const PoseGeom *__r
 int batch_cc(PoseBatch &pb, int npose, const vt_map *target, double threshold, float *d_cc, double *d_sums) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
+  prof_begin(PK_POSE_CC);
   pose_cc_kernel<<<c.sm_count * 8, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, pb.d_grid, pb.cap_grid, target->d,
                                                        target->grid.xsize, target->grid.ysize, pb.d_tab, pb.cap_o,
                                                        pb.cap_items, threshold, pb.d_part);
+  prof_end(PK_POSE_CC);
   VT_LAUNCHED();
   pose_cc_finish_kernel<<<npose, 256, 0, c.stream>>>(pb.d_geom, pb.d_part, pb.cap_items, d_cc, d_sums);
   VT_LAUNCHED();

@@ -107,7 +107,9 @@ static int run_stats(const float *d, long n, float mean, StatOut *host_out) {
   const int grid = stream_grid(n >> 2);
   StatOut *dout = reinterpret_cast<StatOut *>(c.d_scratch);
   double *partials = c.d_scratch + 8;
+  prof_begin(PK_STATS);
   stats_kernel<MODE><<<grid, kThreads, 0, c.stream>>>(d, n, mean, partials, c.d_ticket, dout);
+  prof_end(PK_STATS);
   VT_LAUNCHED();
   StatOut *hp = reinterpret_cast<StatOut *>(c.h_pinned);
   VT_CUDA(cudaMemcpyAsync(hp, dout, sizeof(StatOut), cudaMemcpyDeviceToHost, c.stream));
@@ -194,6 +196,7 @@ int k_unary(UnaryOp op, float *d, long n, float p0, float p1, float p2, double p
   const int grid = stream_grid(n >> 2);
   UnaryParams p{p0, p1, p2, pd};
   cudaStream_t s = ctx().stream;
+  prof_begin(PK_UNARY);
   switch (op) {
     case U_CLAMP: unary_kernel<U_CLAMP><<<grid, kThreads, 0, s>>>(d, n, p); break;
     case U_SCALE: unary_kernel<U_SCALE><<<grid, kThreads, 0, s>>>(d, n, p); break;
@@ -203,6 +206,7 @@ int k_unary(UnaryOp op, float *d, long n, float p0, float p1, float p2, double p
     case U_BINMASK: unary_kernel<U_BINMASK><<<grid, kThreads, 0, s>>>(d, n, p); break;
     case U_MDFFPOT: unary_kernel<U_MDFFPOT><<<grid, kThreads, 0, s>>>(d, n, p); break;
   }
+  prof_end(PK_UNARY);
   VT_LAUNCHED();
   return 0;
 }
