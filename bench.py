@@ -257,7 +257,8 @@ def run_ours(args):
            "best_of_last_step": {"cc": float(best[:, 0].max()), "planted_deg": PLANTED}}
 
     if world == 1:
-        out["cpu_baseline"] = cpu_baseline(pos, radii, com, tmap, poses, budget_s=args.cpu_budget)
+        if not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(pos, radii, com, tmap, poses, budget_s=args.cpu_budget)
         if not args.no_extras:
             out["ops"] = extra_ops(vt, peaks, args)
     print(json.dumps(out))
@@ -450,6 +451,7 @@ def main():
     ap.add_argument("--ops-map", type=int, default=512, help="edge of the maps used by the extra ops legs")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3   # timing rule: at least 3 warm-up steps
