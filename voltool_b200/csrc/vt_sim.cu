@@ -413,19 +413,24 @@ __device__ __forceinline__ int find_pose(const PoseGeom *__restrict__ geo, int n
   return lo;
 }
 
-__global__ void __launch_bounds__(256, 2) splat_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
+constexpr int kWRec = 20;  // floats per warp-staged atom: Ex[8] | dy^2[8] | dz^2[4]
+
+__global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
                                                        int npose, int natoms, int ngroups,
                                                        const float4 *__restrict__ tpos_all,
                                                        const float4 *__restrict__ tgroup_all,
                                                        const float4 *__restrict__ cst, float gs, float invgs,
                                                        float *__restrict__ grid_all, long cap_grid) {
-  __shared__ __align__(16) float s_rec[kChunk * kRec];
-  __shared__ int s_ids[kMaxIds];
+  __shared__ __align__(16) float s_rec[8][32 * kWRec];  // warp-private staged records
+  __shared__ float s_ar[8][32], s_rl2[8][32];           // arinv, (gausslim*sigma)^2 per staged atom
+  __shared__ int s_pend[8][64];                         // warp-private pending ids
+  __shared__ int s_ids[kMaxIds];                        // atoms whose box meets this tile
+  __shared__ unsigned char s_mask[kMaxIds];             // ... and which of the 8 warp regions they meet
   __shared__ int s_cells[256];
   __shared__ int s_wcnt[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned int lt = (1u << lane) - 1u;
   const int wx = warp & 1, wy = (warp >> 1) & 1, wz = warp >> 2;
-  const int ly = wy * 8 + (lane & 7), lz = wz * 4 + (lane >> 3);
   const int total = totals[0];
 
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
@@ -442,90 +447,103 @@ __global__ void __launch_bounds__(256, 2) splat_kernel(const PoseGeom *__restric
     const float bx0 = ox + (x0 - 1) * gs, bx1 = ox + (x0 + kTX) * gs;
     const float by0 = oy + (y0 - 1) * gs, by1 = oy + (y0 + kTY) * gs;
     const float bz0 = oz + (z0 - 1) * gs, bz1 = oz + (z0 + kTZ) * gs;
+    // this warp's 8x8x4 region and this thread's column inside it
+    const int X0 = x0 + wx * 8, Y0 = y0 + wy * 8, Z0 = z0 + wz * 4;
+    const int ly = lane & 7, lz = lane >> 3;
 
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
     int nids = 0;
 
-    // staged compute over s_ids[0..count)
-    auto flush = [&](int count) {
-      for (int c0 = 0; c0 < count; c0 += kChunk) {
-        const int cn = min(kChunk, count - c0);
-        // ---- stage: 4 threads per atom ----
-        {
-          const int slot = tid >> 2, sub = tid & 3;
-          if (slot < cn) {
-            const int id = s_ids[c0 + slot];
-            const float4 a4 = tpos[id];
-            const float4 k4 = cst[id];
-            const float ax = a4.x - ox, ay = a4.y - oy, az = a4.z - oz;  // xyzr = pos - origin
-            const float arinv = k4.x, rl = k4.z;
-            float t = ax * invgs;
-            const int xmin = max(__float2int_rz(t - rl), 0), xmax = min(__float2int_rz(t + rl), nv0 - 1);
-            t = ay * invgs;
-            const int ymin = max(__float2int_rz(t - rl), 0), ymax = min(__float2int_rz(t + rl), nv1 - 1);
-            t = az * invgs;
-            const int zmin = max(__float2int_rz(t - rl), 0), zmax = min(__float2int_rz(t + rl), nv2 - 1);
-            float *rec = s_rec + slot * kRec;
-            if (sub < 2) {
+    // ---- phase 2 (warp-independent): filter the tile list by region, stage 32 atoms at a time
+    //      (lane per atom), accumulate.  No block barrier in here.
+    auto process = [&](int n) {
+      float *rec = s_rec[warp];
+      if (lane < n) {
+        const int id = s_pend[warp][lane];
+        const float4 a4 = tpos[id];
+        const float4 k4 = cst[id];
+        const float ax = a4.x - ox, ay = a4.y - oy, az = a4.z - oz;  // xyzr = pos - origin
+        const float arinv = k4.x, rl = k4.z;
+        float t = ax * invgs;
+        const int xmin = max(__float2int_rz(t - rl), 0), xmax = min(__float2int_rz(t + rl), nv0 - 1);
+        t = ay * invgs;
+        const int ymin = max(__float2int_rz(t - rl), 0), ymax = min(__float2int_rz(t + rl), nv1 - 1);
+        t = az * invgs;
+        const int zmin = max(__float2int_rz(t - rl), 0), zmax = min(__float2int_rz(t + rl), nv2 - 1);
+        float *r = rec + lane * kWRec;
+        float v[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int X = x0 + sub * 8 + k;
-                const float dx = (float)X * gs - ax;
-                const float e = ex2_approx((dx * dx) * arinv);
-                rec[sub * 8 + k] = (X >= xmin && X <= xmax) ? e : 0.0f;
-              }
-            } else if (sub == 2) {
-#pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const int Y = y0 + k;
-                const float dy = (float)Y * gs - ay;
-                rec[16 + k] = (Y >= ymin && Y <= ymax) ? dy * dy : INFINITY;
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int Z = z0 + k;
-                const float dz = (float)Z * gs - az;
-                rec[32 + k] = (Z >= zmin && Z <= zmax) ? dz * dz : INFINITY;
-              }
-              rec[40] = arinv;
-              rec[41] = k4.y;  // radlim^2
-              int mask = 0;
-#pragma unroll
-              for (int w = 0; w < 8; ++w) {
-                const int rx = x0 + (w & 1) * 8, ry = y0 + ((w >> 1) & 1) * 8, rz = z0 + (w >> 2) * 4;
-                const bool hit = xmin <= rx + 7 && xmax >= rx && ymin <= ry + 7 && ymax >= ry && zmin <= rz + 3 && zmax >= rz;
-                mask |= hit ? (1 << w) : 0;
-              }
-              rec[42] = __int_as_float(mask);
-            }
-          }
+        for (int k = 0; k < 8; ++k) {
+          const int X = X0 + k;
+          const float dx = (float)X * gs - ax;
+          const float e = ex2_approx((dx * dx) * arinv);
+          v[k] = (X >= xmin && X <= xmax) ? e : 0.0f;
         }
-        __syncthreads();
-        // ---- compute: each thread 8 x-voxels of one (y,z) ----
-        for (int a = 0; a < cn; ++a) {
-          const float *rec = s_rec + a * kRec;
-          const int mask = __float_as_int(rec[42]);
-          if (!((mask >> warp) & 1)) continue;               // warp-uniform
-          const float d2 = rec[16 + ly] + rec[32 + lz];      // dy*dy + dz*dz
-          const bool pass = d2 < rec[41];                    // !(dy2dz2 >= radlim2)
-          if (!__any_sync(0xffffffffu, pass)) continue;
-          const float e = pass ? ex2_approx(d2 * rec[40]) : 0.0f;
-          const float4 e0 = *reinterpret_cast<const float4 *>(rec + wx * 8);
-          const float4 e1 = *reinterpret_cast<const float4 *>(rec + wx * 8 + 4);
-          acc[0] = __fmaf_rn(e0.x, e, acc[0]); acc[1] = __fmaf_rn(e0.y, e, acc[1]);
-          acc[2] = __fmaf_rn(e0.z, e, acc[2]); acc[3] = __fmaf_rn(e0.w, e, acc[3]);
-          acc[4] = __fmaf_rn(e1.x, e, acc[4]); acc[5] = __fmaf_rn(e1.y, e, acc[5]);
-          acc[6] = __fmaf_rn(e1.z, e, acc[6]); acc[7] = __fmaf_rn(e1.w, e, acc[7]);
+        *reinterpret_cast<float4 *>(r) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(r + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int Y = Y0 + k;
+          const float dy = (float)Y * gs - ay;
+          v[k] = (Y >= ymin && Y <= ymax) ? dy * dy : INFINITY;
         }
-        __syncthreads();
+        *reinterpret_cast<float4 *>(r + 8) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(r + 12) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int Z = Z0 + k;
+          const float dz = (float)Z * gs - az;
+          v[k] = (Z >= zmin && Z <= zmax) ? dz * dz : INFINITY;
+        }
+        *reinterpret_cast<float4 *>(r + 16) = make_float4(v[0], v[1], v[2], v[3]);
+        s_ar[warp][lane] = arinv;
+        s_rl2[warp][lane] = k4.y;
       }
+      __syncwarp();
+      for (int a = 0; a < n; ++a) {
+        const float *r = rec + a * kWRec;
+        const float d2 = r[8 + ly] + r[16 + lz];               // dy*dy + dz*dz
+        const bool pass = d2 < s_rl2[warp][a];                 // !(dy2dz2 >= radlim2)
+        if (!__any_sync(0xffffffffu, pass)) continue;
+        const float e = pass ? ex2_approx(d2 * s_ar[warp][a]) : 0.0f;
+        const float4 e0 = *reinterpret_cast<const float4 *>(r);
+        const float4 e1 = *reinterpret_cast<const float4 *>(r + 4);
+        acc[0] = __fmaf_rn(e0.x, e, acc[0]); acc[1] = __fmaf_rn(e0.y, e, acc[1]);
+        acc[2] = __fmaf_rn(e0.z, e, acc[2]); acc[3] = __fmaf_rn(e0.w, e, acc[3]);
+        acc[4] = __fmaf_rn(e1.x, e, acc[4]); acc[5] = __fmaf_rn(e1.y, e, acc[5]);
+        acc[6] = __fmaf_rn(e1.z, e, acc[6]); acc[7] = __fmaf_rn(e1.w, e, acc[7]);
+      }
+      __syncwarp();
     };
 
+    auto flush = [&](int count) {
+      int have = 0;
+      for (int b0 = 0; b0 < count; b0 += 32) {
+        const int i = b0 + lane;
+        const bool mine = i < count && ((s_mask[i] >> warp) & 1);
+        const unsigned int bal = __ballot_sync(0xffffffffu, mine);
+        if (bal == 0u) continue;
+        if (mine) s_pend[warp][have + __popc(bal & lt)] = s_ids[i];
+        have += __popc(bal);
+        __syncwarp();
+        if (have >= 32) {
+          process(32);
+          const int rest = have - 32;
+          const int keep = lane < rest ? s_pend[warp][32 + lane] : 0;
+          __syncwarp();
+          if (lane < rest) s_pend[warp][lane] = keep;
+          have = rest;
+          __syncwarp();
+        }
+      }
+      if (have > 0) process(have);
+    };
+
+    // ---- phase 1 (block-cooperative): which atoms meet this tile ----
     for (int g0 = 0; g0 < ngroups; g0 += 256) {
-      // ---- cull 256 groups: thread per group, sphere vs tile box ----
+      // cull 256 groups: thread per group, bounding sphere vs tile box
       const int g = g0 + tid;
       bool hit = false;
       if (g < ngroups) {
@@ -541,12 +559,12 @@ __global__ void __launch_bounds__(256, 2) splat_kernel(const PoseGeom *__restric
       int off = 0, nc = 0;
 #pragma unroll
       for (int w = 0; w < 8; ++w) { const int cw = s_wcnt[w]; if (w < warp) off += cw; nc += cw; }
-      if (hit) s_cells[off + __popc(bal & ((1u << lane) - 1u))] = g;
+      if (hit) s_cells[off + __popc(bal & lt)] = g;
       __syncthreads();
-      // ---- exact atom test: warp per surviving group ----
+      // exact atom test: warp per surviving group (the reference's truncated integer box)
       for (int c0 = 0; c0 < nc; c0 += 8) {
         bool take = false;
-        int id = -1;
+        int id = -1, mask = 0;
         if (c0 + warp < nc) {
           id = s_cells[c0 + warp] * 32 + lane;
           if (id < natoms) {
@@ -561,6 +579,15 @@ __global__ void __launch_bounds__(256, 2) splat_kernel(const PoseGeom *__restric
             const int zmin = max(__float2int_rz(t - rl), 0), zmax = min(__float2int_rz(t + rl), nv2 - 1);
             take = xmin <= x0 + kTX - 1 && xmax >= x0 && ymin <= y0 + kTY - 1 && ymax >= y0 && zmin <= z0 + kTZ - 1 &&
                    zmax >= z0 && xmin <= xmax && ymin <= ymax && zmin <= zmax;
+            if (take) {
+              // bit w: box meets warp region w = (wx, wy, wz) = (w&1, (w>>1)&1, w>>2)
+              const int mx = (xmin <= x0 + 7 ? 1 : 0) | (xmax >= x0 + 8 ? 2 : 0);
+              const int my = (ymin <= y0 + 7 ? 1 : 0) | (ymax >= y0 + 8 ? 2 : 0);
+              const int mz = (zmin <= z0 + 3 ? 1 : 0) | (zmax >= z0 + 4 ? 2 : 0);
+#pragma unroll
+              for (int w = 0; w < 8; ++w)
+                if (((mx >> (w & 1)) & 1) && ((my >> ((w >> 1) & 1)) & 1) && ((mz >> (w >> 2)) & 1)) mask |= 1 << w;
+            }
           }
         }
         const unsigned int b2 = __ballot_sync(0xffffffffu, take);
@@ -569,16 +596,24 @@ __global__ void __launch_bounds__(256, 2) splat_kernel(const PoseGeom *__restric
         int o2 = nids, add = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) { const int cw = s_wcnt[w]; if (w < warp) o2 += cw; add += cw; }
-        if (take) s_ids[o2 + __popc(b2 & ((1u << lane) - 1u))] = id;
+        if (take) {
+          const int slot = o2 + __popc(b2 & lt);
+          s_ids[slot] = id;
+          s_mask[slot] = (unsigned char)mask;
+        }
         nids += add;
         __syncthreads();
-        if (nids > kMaxIds - 256) { flush(nids); nids = 0; }
+        if (nids > kMaxIds - 256) {
+          flush(nids);
+          nids = 0;
+          __syncthreads();
+        }
       }
     }
     if (nids > 0) flush(nids);
 
     // ---- every voxel of the tile written exactly once ----
-    const int Y = y0 + ly, Z = z0 + lz, X0 = x0 + wx * 8;
+    const int Y = Y0 + ly, Z = Z0 + lz;
     if (Y < nv1 && Z < nv2) {
       float *row = grid_all + (size_t)p * cap_grid + ((size_t)Z * nv1 + Y) * nv0;
 #pragma unroll
@@ -592,7 +627,7 @@ __global__ void __launch_bounds__(256, 2) splat_kernel(const PoseGeom *__restric
 int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
-  const int grid = c.sm_count * 2 * 4;  // persistent, dynamic enough for uneven tiles
+  const int grid = c.sm_count * 3 * 4;  // persistent: 3 resident CTAs per SM, 4 rounds for uneven tiles
   prof_begin(PK_SPLAT);
   splat_kernel<<<grid, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, as.ngroups, pb.d_tpos, pb.d_tgroup,
                                            as.d_const, as.prm.gs, as.prm.invgs, pb.d_grid, pb.cap_grid);
