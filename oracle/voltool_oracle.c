@@ -1077,8 +1077,15 @@ void vo_fit(float *pos, const float *radii, const float *mass, long natoms, cons
   vo_measure_center(pos, mass, natoms, com);           /* :803 */
   float cc = -1;
   float *bestpos = (float *)malloc(nb), *origin = (float *)malloc(nb);
+  /* table mode only: what framepos holds when a rotate() call starts, and the score of its
+     zero-rotation candidate.  reset_origin() rewrites origin but not framepos (:314-318), so the
+     first candidate after a reset re-scores the OLD origin; the literal loop (direct) does this by
+     construction, the table replay has to be told. */
+  float *frame = (float *)malloc(nb);
+  float frame_cc0 = 0.0f;
   memcpy(origin, pos, nb);
   memcpy(bestpos, pos, nb);
+  memcpy(frame, pos, nb);
   res->n_evaluated = 0;
   for (int k = 0; k < 3; k++) { res->com[k] = com[k]; res->dencom[k] = dencom[k]; }
 
@@ -1093,16 +1100,22 @@ void vo_fit(float *pos, const float *radii, const float *mass, long natoms, cons
     } else {
       float *tab = (float *)malloc(sizeof(float) * (size_t)(m * m * m));
       vo_rotate_table(origin, radii, natoms, com, stride, m, T, t, resolution, tab, 1, 0, nthreads);
+      float fresh_cc0 = tab[0];
+      int stale = memcmp(frame, origin, nb) != 0;
+      if (stale) tab[0] = frame_cc0;
       res->n_evaluated += vo_rotate_replay(tab, m, &cc, &bi);
       if (bi >= 0) {
-        memcpy(bestpos, origin, nb);
+        memcpy(bestpos, (bi == 0 && stale) ? frame : origin, nb);
         vo_pose_transform(bestpos, natoms, com, stride, bi / (m * m), (bi / m) % m, bi % m);
       }
+      memcpy(frame, origin, nb);
+      frame_cc0 = fresh_cc0;
       free(tab);
     }
     res->stage_best[s] = bi;
     if (s == 0 || s == 2) memcpy(origin, bestpos, nb); /* reset_origin :898, :904 */
   }
+  free(frame);
   memcpy(pos, bestpos, nb); /* :911-913 */
   res->best_cc = cc;
   free(bestpos);

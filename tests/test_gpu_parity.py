@@ -317,7 +317,9 @@ def test_fit_matches_oracle(oracle):
     g, t = make_target(oracle, pos, radii, 6.0, 1.2, rot=(48, 24, 312), noise=0.01, seed=42, mass=mass, pad=6)
     # displace the structure so the COM alignment has something to do
     start = pos + np.array([3.0, -2.0, 1.5], np.float32)
-    p_want, r_want = oracle.fit(start, radii, mass, g, t, 6.0, direct=False, nthreads=8)
+    # the LITERAL sequential loop of the reference (calc_cc per visited candidate, skip rule, stale
+    # framepos after reset_origin); one thread so the double sums are in voxel order
+    p_want, r_want = oracle.fit(start, radii, mass, g, t, 6.0, direct=True, nthreads=1)
     p_got, r_got = vt.fit(start, radii, mass, vt.VolMap(G(g), t), 6.0)
     assert list(r_got.stage_best) == list(r_want.stage_best)
     assert r_got.n_evaluated == r_want.n_evaluated

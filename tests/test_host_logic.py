@@ -1,0 +1,198 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads and exports every symbol of
+include/voltool_gpu.h, refuses to compute without a GPU, and its host arithmetic (geometry,
+transforms, skip-rule replay, fit schedule, shard merge) matches the oracle bit for bit."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import voltool_b200 as vt
+from oracle.pyoracle import Grid as OGrid
+from tests.synth import make_structure, make_target
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "voltool_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vt_[a-z0-9_]+)\s*\(", hdr)) - {"vt_table_merge_fn", "vt_table_eval_fn"}
+    assert len(declared) > 50
+    out = subprocess.check_output(["nm", "-D", "--defined-only", vt.lib_path()], text=True)
+    exported = set(re.findall(r" T (vt_[a-z0-9_]+)", out))
+    assert declared <= exported, sorted(declared - exported)
+    L = vt.lib()
+    for name in declared:
+        assert hasattr(L, name)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(vt.VoltoolGpuError):
+        vt.init(0)
+    g = vt.Grid.make((0, 0, 0), (4, 4, 4), 1.0)
+    with pytest.raises(vt.VoltoolGpuError):
+        vt.VolMap(g, np.zeros(64, np.float32))
+
+
+def test_product_does_not_touch_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's cpu legs may use oracle/"""
+    pkg = os.path.join(ROOT, "voltool_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f)).read()
+                for line in text.splitlines():
+                    code = line.split("//")[0].split("#")[0] if not f.endswith(".py") else line.split("#")[0]
+                    assert "pyoracle" not in code and "liboracle" not in code and "voltool_oracle" not in code, (f, line)
+                    if f.endswith(".py"):
+                        assert not re.search(r"^\s*(from|import)\s+oracle", code), (f, line)
+
+
+def test_geometry_matches_oracle(oracle):
+    gs = [OGrid.make((0.0, 0.0, 0.0), (20, 18, 16), 1.0), OGrid.make((0.5, -1.25, 2.0), (17, 21, 13), (1.1, 0.9, 1.3)),
+          OGrid.make((-3.3, 1.7, 0.4), (25, 12, 19), 0.77), OGrid.make((1.0e-3, 5.5, -2.0), (9, 31, 14), (2.0, 0.5, 1.0)),
+          OGrid.make((100.25, -7.5, 33.0), (80, 81, 79), 1.5)]
+    for A in gs:
+        for B in gs:
+            a, b = vt.Grid.from_fields(A), vt.Grid.from_fields(B)
+            assert vt.init_from_intersection(a, b).astuple() == oracle.intersection(A, B).astuple()
+            assert vt.init_from_union(a, b).astuple() == oracle.union(A, B).astuple()
+    assert vt.sim_policy(5.0) == oracle.sim_policy(5.0)
+    assert vt.sim_policy(12.0, 2.0) == oracle.sim_policy(12.0, 2.0)
+
+
+def test_inverse_keeps_structural_zeros(oracle):
+    for g in [OGrid.make((50.3, -20.1, 7.7), (80, 81, 79), 1.5), OGrid.make((-12.345, 33.3, 100.2), (100, 90, 110), (1.0128, 1.0, 0.77))]:
+        for shift in (0, 1):
+            m = oracle.grid_inverse(g, shift).reshape(4, 4)
+            off = m[:3, :3][~np.eye(3, dtype=bool)]
+            assert np.all(off == 0) and np.all(m[:3, 3] == 0) and m[3, 3] == 1.0
+
+
+def test_pose_apply_and_center_match_oracle(oracle):
+    pos, radii, mass = make_structure(700, 11.0, seed=3)
+    com = oracle.measure_center(pos, mass)
+    assert np.array_equal(bits(vt.measure_center(pos, mass)), bits(com))
+    for stride, x, y, z in [(24, 2, 1, 13), (4, 5, 0, 3), (-4, 1, 2, 3), (1, 3, 3, 0), (-1, 0, 0, 1)]:
+        want = oracle.pose_transform(pos, com, stride, x, y, z).reshape(-1, 3)
+        got = vt.pose_apply(pos, com, (stride * x, stride * y, stride * z))
+        assert np.array_equal(bits(got), bits(want))
+
+
+def test_rotate_replay_matches_oracle(oracle):
+    r = np.random.default_rng(5)
+    for m in (4, 6, 15):
+        for trial in range(5):
+            tab = r.random(m ** 3).astype(np.float32)
+            tab[r.integers(0, m ** 3, 5)] = tab[0]  # ties
+            if trial == 4:
+                tab[::7] = np.nan
+            for start in (-1.0, 0.5):
+                assert vt.rotate_replay(tab, m, start) == oracle.rotate_replay(tab, m, start)
+
+
+def _oracle_evaluator(oracle, radii, g, t, res, calls):
+    def ev(origin, com, stride, m, first, step, table):
+        calls.append((stride, m, first, step))
+        full = oracle.rotate_table(origin.copy(), radii, com.copy(), stride, m, g, t, res, nthreads=8, pose_first=first,
+                                   pose_stride=step)
+        idx = np.arange(first, m ** 3, step)
+        table[idx] = full[idx]
+    return ev
+
+
+def test_fit_schedule_matches_oracle_fit(oracle):
+    """the product's schedule (COM alignment, 5 rotate() calls, replay, commit) driven by the oracle's
+    pose evaluator must reproduce the oracle's fit exactly"""
+    pos, radii, mass = make_structure(150, 6.0, seed=9)
+    g, t = make_target(oracle, pos, radii, 8.0, 2.0, rot=(48, 24, 312), noise=0.01, seed=10, mass=mass, pad=3)
+    start = pos + np.array([2.0, -1.0, 0.5], np.float32)
+    p_want, r_want = oracle.fit(start, radii, mass, g, t, 8.0, direct=False, nthreads=8)
+    dencom = oracle.vol_com(g, t)
+    calls = []
+    p_got, r_got = vt.fit_schedule(start, mass, dencom, _oracle_evaluator(oracle, radii, g, t, 8.0, calls))
+    assert [c[:2] for c in calls] == [(24, 15), (4, 6), (-4, 6), (1, 4), (-1, 4)]
+    assert list(r_got.stage_best) == list(r_want.stage_best)
+    assert r_got.n_evaluated == r_want.n_evaluated and r_got.n_computed == 3375 + 432 + 128
+    assert r_got.best_cc == r_want.best_cc
+    assert np.array_equal(bits(p_got), bits(p_want.reshape(-1, 3)))
+    # the literal sequential loop (calc_cc per visited pose) agrees with table + replay.  One thread:
+    # a threaded CC sum differs in the last bit, and the skip rule (cc < best) is sensitive to ties.
+    p_dir, r_dir = oracle.fit(start, radii, mass, g, t, 8.0, direct=True, nthreads=1)
+    assert list(r_dir.stage_best) == list(r_got.stage_best) and r_dir.n_evaluated == r_got.n_evaluated
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+import voltool_b200 as vt
+from voltool_b200 import dist as vdist
+from oracle.pyoracle import Oracle
+from tests.synth import make_structure, make_target
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = vdist.install_shard()
+orc = Oracle()
+pos, radii, mass = make_structure(120, 6.0, seed=19)
+g, t = make_target(orc, pos, radii, 8.0, 2.0, rot=(24, 48, 0), noise=0.01, seed=20, mass=mass, pad=3)
+seen = []
+def ev(origin, com, stride, m, first, step, table):
+    seen.append((first, step))
+    full = orc.rotate_table(origin.copy(), radii, com.copy(), stride, m, g, t, 8.0, nthreads=4, pose_first=first, pose_stride=step)
+    idx = np.arange(first, m ** 3, step)
+    table[idx] = full[idx]
+p, r = vt.fit_schedule(pos, mass, orc.vol_com(g, t), ev)
+assert all(s == (rank, world) for s in seen), seen
+np.save(sys.argv[4] + "/pos%d.npy" % rank, p)
+np.save(sys.argv[4] + "/res%d.npy" % rank, np.array(list(r.stage_best) + [r.n_evaluated], np.int64))
+open(sys.argv[4] + "/cc%d.txt" % rank, "w").write(repr(float(r.best_cc)))
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_sharded_fit_over_gloo(oracle, tmp_path):
+    """world_size 2 on CPU: each rank evaluates every other candidate, the tables are merged with
+    all_gather, both ranks commit the pose the single-process fit commits"""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(tmp_path)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    pos, radii, mass = make_structure(120, 6.0, seed=19)
+    g, t = make_target(oracle, pos, radii, 8.0, 2.0, rot=(24, 48, 0), noise=0.01, seed=20, mass=mass, pad=3)
+    p_want, r_want = oracle.fit(pos, radii, mass, g, t, 8.0, direct=False, nthreads=8)
+    for r in range(2):
+        got = np.load(tmp_path / f"pos{r}.npy")
+        res = np.load(tmp_path / f"res{r}.npy")
+        assert np.array_equal(bits(got), bits(p_want.reshape(-1, 3)))
+        assert list(res[:5]) == list(r_want.stage_best) and res[5] == r_want.n_evaluated
+        assert float(open(tmp_path / f"cc{r}.txt").read()) == float(r_want.best_cc)
+
+
+def test_table_merge_roundtrip_single_process():
+    # world 1 degenerate case of the merge helper's index arithmetic (no process group needed)
+    tab = np.arange(27, dtype=np.float32)
+    for world in (2, 3, 4):
+        per = (27 + world - 1) // world
+        shards = [np.full(per, np.nan, np.float32) for _ in range(world)]
+        for r in range(world):
+            own = tab[r::world]
+            shards[r][:own.size] = own
+        out = np.full(27, np.nan, np.float32)
+        for r in range(world):
+            out[r::world] = shards[r][:out[r::world].size]
+        assert np.array_equal(out, tab)

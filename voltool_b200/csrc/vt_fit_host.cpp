@@ -67,6 +67,13 @@ int vt_fit_schedule(float *pos, const float *mass, long natoms, const float denc
   }
   measure_center(pos, mass, natoms, com);                                   // :803
   std::vector<float> origin(pos, pos + nfl), best(pos, pos + nfl);          // :812-817
+  // rotate() transforms `framepos` in place and restores it from `origin` after every candidate
+  // (:191-195).  reset_origin() (:314-318) rewrites `origin` only, so the FIRST candidate of the
+  // rotate() call that follows a reset still starts from the previous origin: it re-scores the old
+  // origin under the zero rotation.  `frame` tracks what framepos holds when a call starts, and
+  // `frame_cc0` the score of its zero-rotation candidate (candidate 0 of the last table built on it).
+  std::vector<float> frame(pos, pos + nfl);
+  float frame_cc0 = NAN;
   float cc = -1;
   memset(res, 0, sizeof(*res));
   for (int k = 0; k < 3; ++k) { res->com[k] = com[k]; res->dencom[k] = dencom[k]; }
@@ -87,10 +94,13 @@ int vt_fit_schedule(float *pos, const float *mass, long natoms, const float denc
     res->n_computed += total;
     for (int i = 0; i < total; ++i)
       if (table[i] > res->exhaustive_cc) res->exhaustive_cc = table[i];
+    const float fresh_cc0 = table[0];
+    const bool stale = memcmp(frame.data(), origin.data(), sizeof(float) * nfl) != 0;
+    if (stale) table[0] = frame_cc0;
     int bi = -1;
     res->n_evaluated += rotate_replay(table.data(), m, &cc, &bi);
     if (bi >= 0) {                                                           // bestpos <- framepos :181-185
-      best = origin;
+      best = (bi == 0 && stale) ? frame : origin;
       vt_pose pose;
       pose.rot_deg[0] = (float)(stride * (bi / (m * m)));
       pose.rot_deg[1] = (float)(stride * ((bi / m) % m));
@@ -99,6 +109,8 @@ int vt_fit_schedule(float *pos, const float *mass, long natoms, const float denc
       pose_apply(best.data(), natoms, com, pose);
     }
     res->stage_best[s] = bi;
+    frame = origin;                                                          // restored after the last candidate
+    frame_cc0 = fresh_cc0;
     if (s == 0 || s == 2) origin = best;                                     // reset_origin :898, :904
   }
   memcpy(pos, best.data(), sizeof(float) * nfl);                             // :911-913
