@@ -259,68 +259,4 @@ int k_histogram(const float *d, long n, float mn, double binwidthinv, int nbins,
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------ vol_com
-// Voltool.C:229-247 accumulates m*coord into FLOAT accumulators strictly in voxel order (and the
-// mass in double).  A float running sum is order dependent (it even stagnates once the sum's ulp
-// exceeds the addends), and fit() starts from this value, so the order is reproduced literally:
-// one warp walks the map in index order; lanes 0/1/2 own the x/y/z accumulators, lane 3 the mass;
-// all 32 lanes stage the next 1024 voxels into shared memory.
-__global__ void __launch_bounds__(32) vol_com_kernel(const float *__restrict__ d, DevCoord c, double *out) {
-  __shared__ float buf[2][1024];
-  const int lane = threadIdx.x;
-  const long n = (long)c.nx * c.ny * c.nz;
-  float acc = 0.0f;
-  double mass = 0.0;
-  int gx = 0, gy = 0, gz = 0;
-  // lane role: component k of the coordinate
-  const int k = lane < 3 ? lane : 0;
-  const double o = k == 0 ? c.ox : (k == 1 ? c.oy : c.oz);
-  const float xdk = c.xd[k], ydk = c.yd[k], zdk = c.zd[k];
-  long base = 0;
-  int cur = 0;
-  for (int j = lane; j < 1024 && j < n; j += 32) buf[0][j] = d[j];
-  __syncwarp();
-  while (base < n) {
-    const long next = base + 1024;
-    if (next < n)
-      for (int j = lane; j < 1024 && next + j < n; j += 32) buf[cur ^ 1][j] = d[next + j];
-    const int cnt = (int)((n - base) < 1024 ? (n - base) : 1024);
-    if (lane < 4) {
-      for (int j = 0; j < cnt; ++j) {
-        const float m = buf[cur][j];
-        if (lane == 3) {
-          mass = mass + (double)m;
-        } else {
-          const float coord =
-              (float)(((o + (double)((float)gx * xdk)) + (double)((float)gy * ydk)) + (double)((float)gz * zdk));
-          acc = acc + m * coord;
-        }
-        if (++gx == c.nx) { gx = 0; if (++gy == c.ny) { gy = 0; ++gz; } }
-      }
-    }
-    __syncwarp();
-    cur ^= 1;
-    base = next;
-  }
-  if (lane < 3) out[lane] = (double)acc;
-  if (lane == 3) out[3] = mass;
-}
-
-int k_vol_com(const vt_map *m, double out[4]) {
-  VT_REQUIRE_CTX();
-  Ctx &c = ctx();
-  CoordGeom cg;
-  coord_geom(m->grid, cg);
-  DevCoord dc;
-  dc.ox = cg.origin[0]; dc.oy = cg.origin[1]; dc.oz = cg.origin[2];
-  for (int k = 0; k < 3; ++k) { dc.xd[k] = cg.xd[k]; dc.yd[k] = cg.yd[k]; dc.zd[k] = cg.zd[k]; }
-  dc.nx = cg.nx; dc.ny = cg.ny; dc.nz = cg.nz;
-  vol_com_kernel<<<1, 32, 0, c.stream>>>(m->d, dc, c.d_scratch);
-  VT_LAUNCHED();
-  VT_CUDA(cudaMemcpyAsync(c.h_pinned, c.d_scratch, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-  VT_CUDA(cudaStreamSynchronize(c.stream));
-  for (int k = 0; k < 4; ++k) out[k] = c.h_pinned[k];
-  return 0;
-}
-
 }  // namespace vt

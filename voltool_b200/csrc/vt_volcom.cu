@@ -1,0 +1,225 @@
+// vt_volcom.cu -- vol_com (Voltool.C:229-247), bit-exact and parallel.
+//
+// The reference accumulates m_i * coord_i into three FLOAT accumulators strictly in voxel order.
+// A float running sum is order dependent (it even stagnates once its ulp outgrows the addends),
+// and fit() starts from this value, so the sequential semantics must be kept -- but not the
+// sequential cost.  Observation: while the running sum s stays inside one binade (ulp u), every
+// step is  s <- s + rint(a_i / u) * u  (round to nearest; a tie would consult the parity of s).
+// So for a chunk of addends and a given binade the whole chunk collapses to one integer
+//      T_e = sum_i rint(a_i / u_e)
+// valid whenever (1) no a_i / u_e is an exact half-integer and (2) s cannot leave the binade inside
+// the chunk, which  A_e = sum_i |rint(a_i / u_e)|  bounds.
+//
+//   pass 1 (parallel, one CTA per chunk): a_i for the three accumulators, and for 26 candidate
+//           binades starting at ceil(log2(sum |a_i|)) the triple (T_e, A_e, tie).  Above that
+//           window the chunk is the identity (|a_i| < u/2), below it the chunk must be replayed.
+//   pass 2 (one warp, lanes 0..2 = x/y/z): walks the chunks in order; a table hit is O(1), anything
+//           else (binade crossing, tie, zero/subnormal sum) replays that chunk add by add.
+// The result equals the sequential loop bit for bit for any input.  The mass is a double sum
+// (order-insensitive to ~1e-16; the reference adds it in voxel order).
+#include <cstdio>
+#include <cstdlib>
+
+#include "vt_device.cuh"
+
+namespace vt {
+
+constexpr int kBinades = 26;
+
+struct ComEntry {
+  long long T;   // sum of rounded addends, in units of the binade's ulp
+  long long A2;  // (sum of |rounded addends|) << 1 | tie flag
+};
+
+__device__ __forceinline__ float com_addend(const DevCoord &c, int k, float m, int gx, int gy, int gz) {
+  const double o = k == 0 ? c.ox : (k == 1 ? c.oy : c.oz);
+  const float coord =
+      (float)(((o + (double)((float)gx * c.xd[k])) + (double)((float)gy * c.yd[k])) + (double)((float)gz * c.zd[k]));
+  return m * coord;
+}
+
+// pass 1: blockDim = 96 (warp k <-> accumulator k).  Dynamic smem: 3 * L floats.
+__global__ void __launch_bounds__(96) com_tables_kernel(const float *__restrict__ d, long n, DevCoord c, int L,
+                                                        ComEntry *__restrict__ tab, int *__restrict__ emin) {
+  extern __shared__ float s_a[];  // [3][L]
+  const long chunk = blockIdx.x;
+  const long base = chunk * L;
+  const int cnt = (int)((n - base) < L ? (n - base) : L);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long nxy = (long)c.nx * c.ny;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const long idx = base + i;
+    const int gz = (int)(idx / nxy);
+    const long r = idx - (long)gz * nxy;
+    const int gy = (int)(r / c.nx), gx = (int)(r - (long)gy * c.nx);
+    const float m = d[idx];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s_a[k * L + i] = com_addend(c, k, m, gx, gy, gz);
+  }
+  __syncthreads();
+  const float *a = s_a + warp * L;
+  // window start: smallest binade in which the chunk cannot move s by more than ~2^23 ulps
+  double tot = 0.0;
+  for (int i = lane; i < cnt; i += 32) tot += fabs((double)a[i]);
+  tot = warp_sum(tot);
+  int e0;
+  if (!(tot > 0.0)) e0 = -100000;               // all addends zero: identity in every binade
+  else if (!(tot < 1.0e300)) e0 = 100000;       // inf/NaN in the chunk: always replay
+  else { int ex; frexp(tot, &ex); e0 = ex; }    // tot < 2^ex
+  if (lane == 0) emin[chunk * 3 + warp] = e0;
+  if (lane < kBinades && e0 > -100000 && e0 < 100000) {
+    const int e = e0 + lane;
+    const double scale = ldexp(1.0, 23 - e);    // 1 / ulp of binade e
+    long long T = 0, A = 0;
+    int tie = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const double x = (double)a[i] * scale;    // exact
+      const double r = rint(x);
+      tie |= (fabs(x - trunc(x)) == 0.5);
+      const long long ri = (long long)r;
+      T += ri;
+      A += ri < 0 ? -ri : ri;
+    }
+    ComEntry en;
+    en.T = T;
+    en.A2 = (A << 1) | tie;
+    tab[(chunk * 3 + warp) * kBinades + lane] = en;
+  }
+}
+
+// pass 2: one warp.  Lanes 0..2 own the accumulators and take the O(1) table step when they can;
+// when any of them has to replay a chunk, all 32 lanes first rebuild that chunk's addends in shared
+// memory (coalesced loads, parallel coordinate arithmetic) and the owning lane then does only the
+// dependent float adds.
+__global__ void __launch_bounds__(32) com_walk_kernel(const float *__restrict__ d, long n, DevCoord c, int L,
+                                                      long nchunks, const ComEntry *__restrict__ tab,
+                                                      const int *__restrict__ emin, float *__restrict__ out,
+                                                      int *__restrict__ replayed) {
+  extern __shared__ float s_a[];  // [3][L]
+  const int lane = threadIdx.x;
+  const int k = lane < 3 ? lane : 0;
+  float s = 0.0f;
+  int nreplay = 0;
+  const long nxy = (long)c.nx * c.ny;
+  for (long chunk = 0; chunk < nchunks; ++chunk) {
+    bool replay = false;
+    if (lane < 3) {
+      const int e0 = emin[chunk * 3 + k];
+      if (e0 != -100000) {  // else: nothing to add
+        replay = true;
+        const unsigned int bits = __float_as_uint(s);
+        const int ebits = (int)((bits >> 23) & 0xff);
+        if (ebits != 0 && ebits != 0xff && e0 < 100000) {
+          const int j = (ebits - 127) - e0;                  // |s| in [2^e, 2^(e+1)), e = ebits-127
+          const long long S = (long long)(bits & 0x7fffffu) | 0x800000ll;  // |s| / ulp
+          const long long Ss = (bits >> 31) ? -S : S;
+          long long T = 0, A = 0;
+          int tie = 0;
+          bool have = false;
+          if (j >= kBinades) { have = true; }                // every addend rounds to zero
+          else if (j >= 0) {
+            const ComEntry en = tab[(chunk * 3 + k) * kBinades + j];
+            T = en.T; A = en.A2 >> 1; tie = (int)(en.A2 & 1); have = true;
+          }
+          if (have && !tie) {
+            const long long lo = Ss - A, hi = Ss + A;
+            const bool inside =
+                Ss > 0 ? (lo >= 0x800001ll && hi <= 0xfffffell) : (hi <= -0x800001ll && lo >= -0xfffffell);
+            if (inside) {
+              const long long R = Ss + T;
+              const long long Ra = R < 0 ? -R : R;
+              s = __uint_as_float((R < 0 ? 0x80000000u : 0u) | ((unsigned int)ebits << 23) |
+                                  (unsigned int)(Ra & 0x7fffffll));
+              replay = false;
+            }
+          }
+        }
+      }
+    }
+    const unsigned int need = __ballot_sync(0xffffffffu, replay);
+    if (need == 0u) continue;
+    const long base = chunk * L;
+    const int cnt = (int)((n - base) < L ? (n - base) : L);
+    for (int i = lane; i < cnt; i += 32) {
+      const long idx = base + i;
+      const int gz = (int)(idx / nxy);
+      const long r = idx - (long)gz * nxy;
+      const int gy = (int)(r / c.nx), gx = (int)(r - (long)gy * c.nx);
+      const float m = d[idx];
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk)
+        if ((need >> kk) & 1) s_a[kk * L + i] = com_addend(c, kk, m, gx, gy, gz);
+    }
+    __syncwarp();
+    if (replay) {
+      ++nreplay;
+      const float *a = s_a + k * L;
+      int i = 0;
+      for (; i + 16 <= cnt; i += 16) {  // loads batched ahead of the dependent add chain
+        const float4 q0 = *reinterpret_cast<const float4 *>(a + i), q1 = *reinterpret_cast<const float4 *>(a + i + 4);
+        const float4 q2 = *reinterpret_cast<const float4 *>(a + i + 8), q3 = *reinterpret_cast<const float4 *>(a + i + 12);
+        s = s + q0.x; s = s + q0.y; s = s + q0.z; s = s + q0.w;
+        s = s + q1.x; s = s + q1.y; s = s + q1.z; s = s + q1.w;
+        s = s + q2.x; s = s + q2.y; s = s + q2.z; s = s + q2.w;
+        s = s + q3.x; s = s + q3.y; s = s + q3.z; s = s + q3.w;
+      }
+      for (; i < cnt; ++i) s = s + a[i];
+    }
+    __syncwarp();
+  }
+  if (lane < 3) {
+    out[lane] = s;
+    replayed[lane] = nreplay;
+  }
+}
+
+int k_vol_com(const vt_map *m, double out[4]) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  CoordGeom cg;
+  coord_geom(m->grid, cg);
+  DevCoord dc;
+  dc.ox = cg.origin[0]; dc.oy = cg.origin[1]; dc.oz = cg.origin[2];
+  for (int k = 0; k < 3; ++k) { dc.xd[k] = cg.xd[k]; dc.yd[k] = cg.yd[k]; dc.zd[k] = cg.zd[k]; }
+  dc.nx = cg.nx; dc.ny = cg.ny; dc.nz = cg.nz;
+  const long n = m->n;
+  out[0] = out[1] = out[2] = 0.0;
+  out[3] = 0.0;
+  if (n <= 0) return 0;
+  int L = 1024;
+  while (L < 4096 && (n + L - 1) / L > 65536) L *= 2;
+  const long nchunks = (n + L - 1) / L;
+  ComEntry *tab = nullptr;
+  int *emin = nullptr;
+  float *d_out = nullptr;
+  if (dev_alloc((void **)&tab, sizeof(ComEntry) * (size_t)nchunks * 3 * kBinades)) return 2;
+  if (dev_alloc((void **)&emin, sizeof(int) * (size_t)nchunks * 3)) return 2;
+  if (dev_alloc((void **)&d_out, sizeof(float) * 8)) return 2;
+  const size_t smem = sizeof(float) * 3 * (size_t)L;
+  if (smem > 48 * 1024)
+    VT_CUDA(cudaFuncSetAttribute(com_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(PK_STATS);
+  com_tables_kernel<<<(unsigned int)nchunks, 96, smem, c.stream>>>(m->d, n, dc, L, tab, emin);
+  VT_LAUNCHED();
+  if (smem > 48 * 1024)
+    VT_CUDA(cudaFuncSetAttribute(com_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  com_walk_kernel<<<1, 32, smem, c.stream>>>(m->d, n, dc, L, nchunks, tab, emin, d_out, (int *)(d_out + 4));
+  prof_end(PK_STATS);
+  VT_LAUNCHED();
+  float h[8];
+  VT_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  VT_CUDA(cudaStreamSynchronize(c.stream));
+  dev_free(tab); dev_free(emin); dev_free(d_out);
+  for (int k = 0; k < 3; ++k) out[k] = (double)h[k];
+  double mass = 0.0;
+  int rc = k_sum(m->d, n, &mass);
+  if (rc) return rc;
+  out[3] = mass;
+  if (getenv("VOLTOOL_VERBOSE")) {
+    const int *rp = (const int *)(h + 4);
+    fprintf(stderr, "[voltool_gpu] vol_com: %ld chunks of %d, replayed %d/%d/%d\n", nchunks, L, rp[0], rp[1], rp[2]);
+  }
+  return 0;
+}
+
+}  // namespace vt
