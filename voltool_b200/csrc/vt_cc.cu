@@ -117,50 +117,32 @@ static int upload_tables(const DevCoord &C, const DevMap &A, const DevMap &B, Se
   return 0;
 }
 
-constexpr int kZChunk = 16;  // z steps per thread per work item
+constexpr int kZChunk = 32;  // output z steps per warp work item
 
-__global__ void __launch_bounds__(kThreads) cc_sep_kernel(DevMap A, DevMap B, int nx, int ny, int nz,
+__global__ void __launch_bounds__(kThreads, 2) cc_sep_kernel(DevMap A, DevMap B, int nx, int ny, int nz,
                                                           const AxisEntry *__restrict__ T, int offAx, int offAy,
-                                                          int offAz, int offBx, int offBy, int offBz, double thr,
+                                                          int offAz, int offBx, int offBy, int offBz, float thr_f,
                                                           double *partials, unsigned int *ticket, double *out) {
   __shared__ double sm[6 * 32];
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-  // work item = (32-wide x tile, gy, z chunk), dealt to warps round-robin (x tile fastest)
+  CcAcc a;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) a.s[k] = 0.0;
+  a.n = 0;
+  // work item = (32-wide x tile, kRows y rows, z chunk), dealt to warps round-robin (x tile fastest)
   const int xtiles = (nx + 31) >> 5;
+  const int ygroups = (ny + kRows - 1) / kRows;
   const int zchunks = (nz + kZChunk - 1) / kZChunk;
-  const long work = (long)xtiles * ny * zchunks;
-  const long planeA = (long)A.nx * A.ny, planeB = (long)B.nx * B.ny;
+  const long work = (long)xtiles * ygroups * zchunks;
   const int lane = threadIdx.x & 31;
   const long wstride = (long)gridDim.x * (kThreads / 32);
   for (long w = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); w < work; w += wstride) {
     const int xb = (int)(w % xtiles);
     const long r = w / xtiles;
-    const int gy = (int)(r % ny), zc = (int)(r / ny);
-    const int gx = xb * 32 + lane;
-    if (gx >= nx) continue;
-    const AxisEntry ax = T[offAx + gx], ay = T[offAy + gy];
-    const AxisEntry bx = T[offBx + gx], by = T[offBy + gy];
-    const bool inA = ax.inside && ay.inside, inB = bx.inside && by.inside;
-    if (!inA || !inB) continue;  // one of the samples would be NaN for every z
-    const long a_row0 = (long)ay.i0 * A.nx, a_row1 = (long)ay.i1 * A.nx;
-    const long b_row0 = (long)by.i0 * B.nx, b_row1 = (long)by.i1 * B.nx;
-    PlaneCache pa, pb;
-    double fA = 0.0, fB = 0.0, fAA = 0.0, fBB = 0.0, fAB = 0.0;  // MDFF.C:79-83: double sums of float terms
-    int cnt = 0;
-    const int zend = min(nz, (zc + 1) * kZChunk);
-    for (int gz = zc * kZChunk; gz < zend; ++gz) {
-      const AxisEntry az = T[offAz + gz], bz = T[offBz + gz];
-      if (!az.inside || !bz.inside) continue;
-      const float vA = sep_sample(A.d, planeA, a_row0, a_row1, ax.i0, ax.i1, ax.f, ay.f, az, pa);
-      if (is_nan_bits(vA) || !((double)vA >= thr)) continue;
-      const float vB = sep_sample(B.d, planeB, b_row0, b_row1, bx.i0, bx.i1, bx.f, by.f, bz, pb);
-      if (is_nan_bits(vB)) continue;
-      fA += (double)vA; fB += (double)vB; fAA += (double)(vA * vA); fBB += (double)(vB * vB); fAB += (double)(vA * vB);
-      ++cnt;
-    }
-    acc[0] += fA; acc[1] += fB; acc[2] += fAA; acc[3] += fBB; acc[4] += fAB;
-    acc[5] += (double)cnt;
+    const int yg = (int)(r % ygroups), zc = (int)(r / ygroups);
+    cc_march_item(A.d, A.nx, A.ny, B.d, B.nx, B.ny, T + offAx, T + offAy, T + offAz, T + offBx, T + offBy, T + offBz, nx,
+                  ny, xb * 32 + lane, yg * kRows, zc * kZChunk, min(nz, (zc + 1) * kZChunk), thr_f, a);
   }
+  double acc[6] = {a.s[0], a.s[1], a.s[2], a.s[3], a.s[4], (double)a.n};
   block_sum<6>(acc, sm);
   grid_finish<6>(acc, partials, ticket, out, sm);
 }
@@ -189,12 +171,12 @@ int k_cc(const vt_map *A, const vt_map *B, double thr, double sums[5], long *n) 
     SepTables T;
     int rc = upload_tables(dC, dA, dB, T);
     if (rc) return rc;
-    const long work = (long)((og.xsize + 31) / 32) * og.ysize * ((og.zsize + kZChunk - 1) / kZChunk);
+    const long work = (long)((og.xsize + 31) / 32) * ((og.ysize + kRows - 1) / kRows) * ((og.zsize + kZChunk - 1) / kZChunk);
     const long wblocks = (work + kThreads / 32 - 1) / (kThreads / 32);
     int grid = (int)(wblocks < (long)c.sm_count * 8 ? wblocks : (long)c.sm_count * 8);
     prof_begin(PK_CC);
     cc_sep_kernel<<<grid, kThreads, 0, c.stream>>>(dA, dB, og.xsize, og.ysize, og.zsize, T.d, T.offAx, T.offAy, T.offAz,
-                                                   T.offBx, T.offBy, T.offBz, thr, partials, c.d_ticket, dout);
+                                                   T.offBx, T.offBy, T.offBz, threshold_as_float(thr), partials, c.d_ticket, dout);
     prof_end(PK_CC);
     VT_LAUNCHED();
     dev_free(T.d);

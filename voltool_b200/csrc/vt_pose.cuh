@@ -23,7 +23,7 @@ constexpr int kTX = 16, kTY = 16, kTZ = 8;
 constexpr int kChunk = 64;     // atoms staged per compute round
 constexpr int kRec = 44;       // floats per staged atom record
 constexpr int kMaxIds = 2048;  // gathered atom ids per flush
-constexpr int kZChunkFit = 16;
+constexpr int kZChunkFit = 32;
 
 // per-pose geometry, written by pose_setup_kernel
 struct PoseGeom {

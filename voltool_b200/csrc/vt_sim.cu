@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) pose_setup_kernel(const unsigned int *__r
         G.od[0] = xd[0]; G.od[1] = yd[1]; G.od[2] = zd[2];
         G.cc_xt = (og.xsize + 31) / 32;
         G.cc_zc = (og.zsize + kZChunkFit - 1) / kZChunkFit;
-        G.cc_items = G.cc_xt * og.ysize * G.cc_zc;
+        G.cc_items = G.cc_xt * ((og.ysize + kRows - 1) / kRows) * G.cc_zc;
       }
     }
     out[p] = G;
@@ -637,50 +637,31 @@ int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
 }
 
 // ------------------------------------------------------------------------------------------ batched cc
-__global__ void __launch_bounds__(256) pose_cc_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
+__global__ void __launch_bounds__(256, 2) pose_cc_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
                                                       int npose, const float *__restrict__ grid_all, long cap_grid,
                                                       const float *__restrict__ tdata, int tnx, int tny,
                                                       const geom::AxisEntry *__restrict__ tab_all, int cap_o,
-                                                      long cap_items, double thr, double *__restrict__ part) {
+                                                      long cap_items, float thr_f, double *__restrict__ part) {
   const int lane = threadIdx.x & 31;
   const int total = totals[1];
   const int wstride = gridDim.x * 8;
-  const long planeB = (long)tnx * tny;
   for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < total; item += wstride) {
     const int p = find_pose(geo, npose, item, true);
     const PoseGeom &G = geo[p];
     const int local = item - G.cc_base;
     const int xb = local % G.cc_xt;
     const int r = local / G.cc_xt;
-    const int gy = r % G.no[1], zc = r / G.no[1];
-    const int gx = xb * 32 + lane;
+    const int ygroups = (G.no[1] + kRows - 1) / kRows;
+    const int yg = r % ygroups, zc = r / ygroups;
     const geom::AxisEntry *__restrict__ T = tab_all + (size_t)p * 6 * cap_o;
-    const float *__restrict__ A = grid_all + (size_t)p * cap_grid;
-    const int anx = G.nv[0];
-    const long planeA = (long)anx * G.nv[1];
-    double fA = 0.0, fB = 0.0, fAA = 0.0, fBB = 0.0, fAB = 0.0;  // MDFF.C:79-83: double sums of float terms
-    int cnt = 0;
-    if (gx < G.no[0]) {
-      const geom::AxisEntry ax = T[gx], ay = T[cap_o + gy];
-      const geom::AxisEntry bx = T[3 * cap_o + gx], by = T[4 * cap_o + gy];
-      if (ax.inside && ay.inside && bx.inside && by.inside) {
-        const long a_row0 = (long)ay.i0 * anx, a_row1 = (long)ay.i1 * anx;
-        const long b_row0 = (long)by.i0 * tnx, b_row1 = (long)by.i1 * tnx;
-        PlaneCache pa, pb;
-        const int zend = min(G.no[2], (zc + 1) * kZChunkFit);
-        for (int gz = zc * kZChunkFit; gz < zend; ++gz) {
-          const geom::AxisEntry az = T[2 * cap_o + gz], bz = T[5 * cap_o + gz];
-          if (!az.inside || !bz.inside) continue;
-          const float vA = sep_sample(A, planeA, a_row0, a_row1, ax.i0, ax.i1, ax.f, ay.f, az, pa);
-          if (is_nan_bits(vA) || !((double)vA >= thr)) continue;
-          const float vB = sep_sample(tdata, planeB, b_row0, b_row1, bx.i0, bx.i1, bx.f, by.f, bz, pb);
-          if (is_nan_bits(vB)) continue;
-          fA += (double)vA; fB += (double)vB; fAA += (double)(vA * vA); fBB += (double)(vB * vB); fAB += (double)(vA * vB);
-          ++cnt;
-        }
-      }
-    }
-    double v[6] = {fA, fB, fAA, fBB, fAB, (double)cnt};
+    CcAcc a;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) a.s[k] = 0.0;
+    a.n = 0;
+    cc_march_item(grid_all + (size_t)p * cap_grid, G.nv[0], G.nv[1], tdata, tnx, tny, T, T + cap_o, T + 2 * cap_o,
+                  T + 3 * cap_o, T + 4 * cap_o, T + 5 * cap_o, G.no[0], G.no[1], xb * 32 + lane, yg * kRows,
+                  zc * kZChunkFit, min(G.no[2], (zc + 1) * kZChunkFit), thr_f, a);
+    double v[6] = {a.s[0], a.s[1], a.s[2], a.s[3], a.s[4], (double)a.n};
 #pragma unroll
     for (int k = 0; k < 6; ++k) v[k] = warp_sum(v[k]);
     if (lane == 0) {
@@ -727,7 +708,7 @@ int batch_cc(PoseBatch &pb, int npose, const vt_map *target, double threshold, f
   prof_begin(PK_POSE_CC);
   pose_cc_kernel<<<c.sm_count * 8, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, pb.d_grid, pb.cap_grid, target->d,
                                                        target->grid.xsize, target->grid.ysize, pb.d_tab, pb.cap_o,
-                                                       pb.cap_items, threshold, pb.d_part);
+                                                       pb.cap_items, threshold_as_float(threshold), pb.d_part);
   prof_end(PK_POSE_CC);
   VT_LAUNCHED();
   pose_cc_finish_kernel<<<npose, 256, 0, c.stream>>>(pb.d_geom, pb.d_part, pb.cap_items, d_cc, d_sums);
