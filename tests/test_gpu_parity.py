@@ -82,6 +82,28 @@ def test_cc_generic_path_matches(oracle, monkeypatch):
     assert abs(got - want) <= 1e-9
 
 
+def test_cc_staged_ring_path(oracle, monkeypatch):
+    """the cp.async.bulk / mbarrier ring variant (forced here on small maps): same samples, sums formed
+    in float per 4 voxels -> 1e-7 on CC; falls back to the direct kernel when its preconditions fail"""
+    r = np.random.default_rng(11)
+    cases = [(OGrid.make((0, 0, 0), (96, 70, 150), 1.0), OGrid.make((0, 0, 0), (96, 70, 150), 1.0)),      # identical
+             (OGrid.make((0, 0, 0), (128, 64, 90), 1.0), OGrid.make((0.5, -3.0, 2.25), (132, 60, 96), 1.0)),  # offset
+             (OGrid.make((1.0, 2.0, 3.0), (80, 81, 79), 1.5), OGrid.make((0, 0, 0), (128, 128, 128), 1.0)),  # fit-like
+             (OGrid.make((0, 0, 0), (100, 40, 40), 1.0), OGrid.make((0.3, 0.2, 0.1), (60, 44, 48), 0.9))]   # nx % 4 != 0
+    for A, B in cases:
+        a, b = r.random(A.n, dtype=np.float32), r.random(B.n, dtype=np.float32)
+        b[::1013] = np.nan
+        for thr in (-FLT_MAX, 0.4):
+            want, nw, _ = oracle.cc(A, a, B, b, thr, full=True)
+            monkeypatch.setenv("VOLTOOL_CC_STAGED", "1")
+            got, ng, _ = vt.cc_threaded(vt.VolMap(G(A), a), vt.VolMap(G(B), b), thr, full=True)
+            monkeypatch.setenv("VOLTOOL_CC_STAGED", "0")
+            ref, nr, _ = vt.cc_threaded(vt.VolMap(G(A), a), vt.VolMap(G(B), b), thr, full=True)
+            monkeypatch.delenv("VOLTOOL_CC_STAGED")
+            assert ng == nw == nr
+            assert abs(ref - want) <= 1e-9 and abs(got - want) <= 1e-7, (got, ref, want)
+
+
 def test_cc_known_answers():
     g = vt.Grid.make((0, 0, 0), (64, 60, 56), 1.0)
     a = rng_map(5, g.n)

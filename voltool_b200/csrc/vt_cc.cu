@@ -94,10 +94,18 @@ static bool finite_geom(const DevCoord &c) {
 struct SepTables {
   AxisEntry *d = nullptr;  // [Ax | Ay | Az | Bx | By | Bz]
   int offAx, offAy, offAz, offBx, offBy, offBz;
+  std::vector<AxisEntry> host;
+  int off[6];
 };
 
+int k_cc_staged(const DevMap &A, const DevMap &B, int nx, int ny, int nz, const std::vector<AxisEntry> &host_tab,
+                const int off[6], const AxisEntry *d_tab, float thr_f, double *partials, unsigned int *ticket,
+                double *dout);
+
 static int upload_tables(const DevCoord &C, const DevMap &A, const DevMap &B, SepTables &T) {
-  std::vector<AxisEntry> all, t;
+  std::vector<AxisEntry> &all = T.host;
+  std::vector<AxisEntry> t;
+  all.clear();
   const DevMap *maps[2] = {&A, &B};
   int offs[6];
   for (int m = 0; m < 2; ++m) {
@@ -111,9 +119,10 @@ static int upload_tables(const DevCoord &C, const DevMap &A, const DevMap &B, Se
   }
   T.offAx = offs[0]; T.offAy = offs[1]; T.offAz = offs[2];
   T.offBx = offs[3]; T.offBy = offs[4]; T.offBz = offs[5];
+  for (int k = 0; k < 6; ++k) T.off[k] = offs[k];
   if (dev_alloc((void **)&T.d, sizeof(AxisEntry) * (all.size() + 1))) return 2;
   VT_CUDA(cudaMemcpyAsync(T.d, all.data(), sizeof(AxisEntry) * all.size(), cudaMemcpyHostToDevice, ctx().stream));
-  VT_CUDA(cudaStreamSynchronize(ctx().stream));  // `all` is pageable and about to go out of scope
+  VT_CUDA(cudaStreamSynchronize(ctx().stream));  // pageable source
   return 0;
 }
 
@@ -171,14 +180,25 @@ int k_cc(const vt_map *A, const vt_map *B, double thr, double sums[5], long *n) 
     SepTables T;
     int rc = upload_tables(dC, dA, dB, T);
     if (rc) return rc;
-    const long work = (long)((og.xsize + 31) / 32) * ((og.ysize + kRows - 1) / kRows) * ((og.zsize + kZChunk - 1) / kZChunk);
-    const long wblocks = (work + kThreads / 32 - 1) / (kThreads / 32);
-    int grid = (int)(wblocks < (long)c.sm_count * 8 ? wblocks : (long)c.sm_count * 8);
-    prof_begin(PK_CC);
-    cc_sep_kernel<<<grid, kThreads, 0, c.stream>>>(dA, dB, og.xsize, og.ysize, og.zsize, T.d, T.offAx, T.offAy, T.offAz,
-                                                   T.offBx, T.offBy, T.offBz, threshold_as_float(thr), partials, c.d_ticket, dout);
-    prof_end(PK_CC);
-    VT_LAUNCHED();
+    // large maps stream through the shared-memory ring (vt_cc_staged.cu); small ones and anything
+    // its preconditions reject take the direct kernel
+    const char *force = getenv("VOLTOOL_CC_STAGED");
+    const bool want_staged = force ? atoi(force) != 0 : vox >= (8L << 20);
+    int st = 1;
+    if (want_staged)
+      st = k_cc_staged(dA, dB, og.xsize, og.ysize, og.zsize, T.host, T.off, T.d, threshold_as_float(thr), partials,
+                       c.d_ticket, dout);
+    if (st > 1) return st;
+    if (st == 1) {
+      const long work = (long)((og.xsize + 31) / 32) * ((og.ysize + kRows - 1) / kRows) * ((og.zsize + kZChunk - 1) / kZChunk);
+      const long wblocks = (work + kThreads / 32 - 1) / (kThreads / 32);
+      int grid = (int)(wblocks < (long)c.sm_count * 8 ? wblocks : (long)c.sm_count * 8);
+      prof_begin(PK_CC);
+      cc_sep_kernel<<<grid, kThreads, 0, c.stream>>>(dA, dB, og.xsize, og.ysize, og.zsize, T.d, T.offAx, T.offAy, T.offAz,
+                                                     T.offBx, T.offBy, T.offBz, threshold_as_float(thr), partials, c.d_ticket, dout);
+      prof_end(PK_CC);
+      VT_LAUNCHED();
+    }
     dev_free(T.d);
   } else {
     const long rows = (long)og.ysize * og.zsize;

@@ -1,0 +1,339 @@
+// vt_cc_staged.cu -- HBM-streaming variant of the separable CC kernel for large maps.
+//
+// The direct kernel (vt_cc.cu / vt_sep.cuh) loads source rows straight into registers; with ~1 us of
+// loaded HBM latency and a dependent chain per z step it cannot keep enough bytes in flight.  Here
+// the loads are decoupled from the arithmetic: two producer warps stream whole source-plane boxes
+// (rows of the tile + halo) into a shared-memory ring with cp.async.bulk (the TMA copy engine,
+// completion on mbarriers), several planes ahead; eight consumer warps take planes from the ring,
+// form the bilinear value of their rows once per plane and march in z exactly like the direct
+// kernel.  Same table-driven arithmetic (bit-identical samples); the five sums are formed in float
+// over the Y rows of one z step before they are added in double, so CC agrees with the direct path
+// to ~1e-8 rather than 1e-12.  Selected for large grids only (or VOLTOOL_CC_STAGED=1).
+#include <cstdlib>
+#include <vector>
+
+#include "vt_device.cuh"
+#include "vt_geom.h"
+#include "vt_sep.cuh"
+
+namespace vt {
+namespace staged {
+
+constexpr int TX = 64;       // output x per CTA tile (2 warps x 32 lanes)
+constexpr int XS = 72;       // floats per staged source row (TX + 1 halo + 16-byte alignment slack)
+constexpr int S = 4;         // ring stages per map
+constexpr int kConsumers = 8;
+constexpr int kThreadsStaged = (kConsumers + 2) * 32;
+
+template <int Y> struct Shape {
+  static constexpr int TY = 4 * Y;     // 4 warp rows x Y rows per thread
+  static constexpr int YS = TY + 4;    // staged source rows per plane (TY + 1 halo + slack)
+};
+
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct Box {  // source box of one tile in one map
+  int xb, wfl;   // first staged x (multiple of 4), floats per row (multiple of 4)
+  int yb, nrows;
+};
+
+__device__ __forceinline__ Box tile_box(const AxisEntry *__restrict__ tx, const AxisEntry *__restrict__ ty, int gx0,
+                                        int gx1, int gy0, int gy1, int src_nx) {
+  Box b;
+  b.xb = tx[gx0].i0 & ~3;
+  int w = (tx[gx1].i1 - b.xb + 1 + 3) & ~3;
+  if (b.xb + w > src_nx) w = src_nx - b.xb;
+  b.wfl = w;
+  b.yb = ty[gy0].i0;
+  b.nrows = ty[gy1].i1 - b.yb + 1;
+  return b;
+}
+
+template <int Y>
+struct Consumer {
+  int x0l, x1l;
+  float xf;
+  int r0l[Y], r1l[Y];
+  float yf[Y];
+  unsigned int loadmask;
+  int z0, z1;
+  float lo[Y], hi[Y];
+};
+
+template <int Y>
+__device__ __forceinline__ void consumer_init(Consumer<Y> &c, const AxisEntry &ex, const AxisEntry *__restrict__ ty,
+                                              int gy0, int ny_out, const Box &b) {
+  c.x0l = ex.i0 - b.xb; c.x1l = ex.i1 - b.xb; c.xf = ex.f;
+  c.loadmask = 0u;
+#pragma unroll
+  for (int r = 0; r < Y; ++r) {
+    const AxisEntry ey = ty[min(gy0 + r, ny_out - 1)];
+    c.r0l[r] = (ey.i0 - b.yb) * XS;
+    c.r1l[r] = (ey.i1 - b.yb) * XS;
+    c.yf[r] = ey.f;
+    if (r == 0 || c.r0l[r] != c.r1l[r - 1]) c.loadmask |= 1u << (2 * r);
+    if (c.r1l[r] != c.r0l[r]) c.loadmask |= 1u << (2 * r + 1);
+  }
+  c.z0 = -1; c.z1 = -1;
+}
+
+// bilinear values of the staged plane for this thread's rows (same expressions as march_plane)
+template <int Y>
+__device__ __forceinline__ void consumer_plane(const Consumer<Y> &c, const float *__restrict__ P, float (&out)[Y]) {
+  float prev_xl = 0.f;
+#pragma unroll
+  for (int r = 0; r < Y; ++r) {
+    float xa, xb;
+    if ((c.loadmask >> (2 * r)) & 1) {
+      const float v0 = P[c.r0l[r] + c.x0l], v1 = P[c.r0l[r] + c.x1l];
+      xa = v0 + c.xf * (v1 - v0);
+    } else {
+      xa = prev_xl;
+    }
+    if ((c.loadmask >> (2 * r + 1)) & 1) {
+      const float v0 = P[c.r1l[r] + c.x0l], v1 = P[c.r1l[r] + c.x1l];
+      xb = v0 + c.xf * (v1 - v0);
+    } else {
+      xb = xa;
+    }
+    prev_xl = xb;
+    out[r] = xa + c.yf[r] * (xb - xa);
+  }
+}
+
+// take the next plane of this map's ring (planes arrive strictly in order)
+template <int Y>
+__device__ __forceinline__ void consumer_take(const Consumer<Y> &c, const float *__restrict__ ring,
+                                              unsigned long long *full, unsigned long long *empty, unsigned int &cnt,
+                                              int plane_floats, float (&out)[Y]) {
+  const unsigned int slot = cnt % S, par = (cnt / S) & 1u;
+  mbar_wait(&full[slot], par);
+  consumer_plane<Y>(c, ring + (size_t)slot * plane_floats, out);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);
+  ++cnt;
+}
+
+template <int Y>
+__device__ __forceinline__ void consumer_sample(Consumer<Y> &c, const AxisEntry &ez, const float *__restrict__ ring,
+                                                unsigned long long *full, unsigned long long *empty, unsigned int &cnt,
+                                                int plane_floats, float (&v)[Y]) {
+  if (ez.i0 == c.z1 && ez.i0 != c.z0) {
+#pragma unroll
+    for (int r = 0; r < Y; ++r) { const float t = c.lo[r]; c.lo[r] = c.hi[r]; c.hi[r] = t; }
+    const int t = c.z0; c.z0 = c.z1; c.z1 = t;
+  }
+  if (ez.i0 != c.z0) { consumer_take<Y>(c, ring, full, empty, cnt, plane_floats, c.lo); c.z0 = ez.i0; }
+  if (ez.i1 == c.z0) {
+#pragma unroll
+    for (int r = 0; r < Y; ++r) c.hi[r] = c.lo[r];
+    c.z1 = c.z0;
+  } else if (ez.i1 != c.z1) {
+    consumer_take<Y>(c, ring, full, empty, cnt, plane_floats, c.hi);
+    c.z1 = ez.i1;
+  }
+#pragma unroll
+  for (int r = 0; r < Y; ++r) v[r] = c.lo[r] + ez.f * (c.hi[r] - c.lo[r]);
+}
+
+__device__ __forceinline__ void producer_run(const float *__restrict__ src, int snx, int sny, const Box &b, int p0,
+                                             int p1, float *ring, unsigned long long *full, unsigned long long *empty,
+                                             unsigned int &cnt, int plane_floats) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int wbytes = (unsigned int)b.wfl * 4u;
+  for (int p = p0; p <= p1; ++p) {
+    const unsigned int slot = cnt % S, par = ((cnt / S) & 1u) ^ 1u;
+    mbar_wait(&empty[slot], par);
+    if (lane == 0) mbar_expect_tx(&full[slot], wbytes * (unsigned int)b.nrows);
+    __syncwarp();
+    float *dst = ring + (size_t)slot * plane_floats;
+    const float *g = src + ((size_t)p * sny + b.yb) * snx + b.xb;
+    for (int r = lane; r < b.nrows; r += 32) bulk_g2s(dst + r * XS, g + (size_t)r * snx, wbytes, &full[slot]);
+    ++cnt;
+  }
+}
+
+template <int Y>
+__global__ void __launch_bounds__(kThreadsStaged, 2)
+    cc_staged_kernel(const float *__restrict__ A, int anx, int any, const float *__restrict__ B, int bnx, int bny,
+                     const AxisEntry *__restrict__ tAx, const AxisEntry *__restrict__ tAy,
+                     const AxisEntry *__restrict__ tAz, const AxisEntry *__restrict__ tBx,
+                     const AxisEntry *__restrict__ tBy, const AxisEntry *__restrict__ tBz, int nx, int ny, int nz,
+                     int zchunk, int zlo, int zhi, float thr_f, double *partials, unsigned int *ticket, double *out) {
+  constexpr int TY = Shape<Y>::TY, YS = Shape<Y>::YS;
+  constexpr int plane_floats = YS * XS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *ringA = reinterpret_cast<float *>(smem_raw);
+  float *ringB = ringA + (size_t)S * plane_floats;
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ringB + (size_t)S * plane_floats);
+  unsigned long long *fullA = bars, *emptyA = bars + S, *fullB = bars + 2 * S, *emptyB = bars + 3 * S;
+  __shared__ double sm[6 * 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&fullA[s], 1); mbar_init(&fullB[s], 1);
+      mbar_init(&emptyA[s], kConsumers); mbar_init(&emptyB[s], kConsumers);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  unsigned int cntA = 0, cntB = 0;
+  const int xtiles = (nx + TX - 1) / TX, ytiles = (ny + TY - 1) / TY;
+  const int zchunks = (zhi - zlo + zchunk - 1) / zchunk;
+  const long work = (long)xtiles * ytiles * zchunks;
+  for (long w = blockIdx.x; w < work; w += gridDim.x) {
+    const int xt = (int)(w % xtiles);
+    const long rr = w / xtiles;
+    const int yt = (int)(rr % ytiles), zc = (int)(rr / ytiles);
+    const int gx_first = xt * TX, gx_last = min(nx - 1, gx_first + TX - 1);
+    const int gy_first = yt * TY, gy_last = min(ny - 1, gy_first + TY - 1);
+    const int za = zlo + zc * zchunk, zb = min(zhi, za + zchunk);  // every z in [zlo, zhi) is inside both maps
+    const Box bA = tile_box(tAx, tAy, gx_first, gx_last, gy_first, gy_last, anx);
+    const Box bB = tile_box(tBx, tBy, gx_first, gx_last, gy_first, gy_last, bnx);
+    if (warp == kConsumers) {
+      producer_run(A, anx, any, bA, tAz[za].i0, tAz[zb - 1].i1, ringA, fullA, emptyA, cntA, plane_floats);
+    } else if (warp == kConsumers + 1) {
+      producer_run(B, bnx, bny, bB, tBz[za].i0, tBz[zb - 1].i1, ringB, fullB, emptyB, cntB, plane_floats);
+    } else {
+      const int gx = gx_first + (warp & 1) * 32 + lane;
+      const int gy0 = gy_first + (warp >> 1) * Y;
+      const int gxc = min(gx, nx - 1);
+      const AxisEntry ax = tAx[gxc], bx = tBx[gxc];
+      Consumer<Y> ca, cb;
+      consumer_init<Y>(ca, ax, tAy, gy0, ny, bA);
+      consumer_init<Y>(cb, bx, tBy, gy0, ny, bB);
+      bool ok[Y];
+#pragma unroll
+      for (int r = 0; r < Y; ++r) {
+        const int gy = gy0 + r, gyc = min(gy, ny - 1);
+        ok[r] = gx < nx && gy < ny && ax.inside && bx.inside && tAy[gyc].inside && tBy[gyc].inside;
+      }
+      for (int gz = za; gz < zb; ++gz) {
+        const AxisEntry az = tAz[gz], bz = tBz[gz];
+        float va[Y], vb[Y];
+        consumer_sample<Y>(ca, az, ringA, fullA, emptyA, cntA, plane_floats, va);
+        consumer_sample<Y>(cb, bz, ringB, fullB, emptyB, cntB, plane_floats, vb);
+        float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < Y; ++r) {
+          const bool take = ok[r] && (va[r] == va[r]) && (va[r] >= thr_f) && (vb[r] == vb[r]);  // MDFF.C:73-77
+          const float a = take ? va[r] : 0.f, b = take ? vb[r] : 0.f;
+          fA += a; fB += b;
+          fAA += a * a; fBB += b * b; fAB += a * b;
+          cnt += take ? 1 : 0;
+        }
+        acc[0] += (double)fA; acc[1] += (double)fB; acc[2] += (double)fAA; acc[3] += (double)fBB; acc[4] += (double)fAB;
+        acc[5] += (double)cnt;
+      }
+    }
+  }
+  block_sum<6>(acc, sm);
+  grid_finish<6>(acc, partials, ticket, out, sm);
+}
+
+}  // namespace staged
+
+// Host: is the staged kernel applicable to these tables?  `tab` = [Ax|Ay|Az|Bx|By|Bz] with offsets.
+template <int Y>
+static bool staged_ok(const std::vector<AxisEntry> &tab, const int off[6], int nx, int ny, int nz, int anx, int bnx,
+                      int &zlo, int &zhi) {
+  using namespace staged;
+  constexpr int TY = Shape<Y>::TY, YS = Shape<Y>::YS;
+  if ((anx & 3) || (bnx & 3) || nx < 1 || ny < 1 || nz < 1) return false;
+  const int srcnx[2] = {anx, bnx};
+  for (int m = 0; m < 2; ++m) {
+    const AxisEntry *tx = &tab[off[3 * m]], *ty = &tab[off[3 * m + 1]], *tz = &tab[off[3 * m + 2]];
+    for (int g = 1; g < nx; ++g) if (tx[g].i0 < tx[g - 1].i0 || tx[g].i1 < tx[g - 1].i1) return false;
+    for (int g = 1; g < ny; ++g) if (ty[g].i0 < ty[g - 1].i0 || ty[g].i1 < ty[g - 1].i1) return false;
+    for (int g0 = 0; g0 < nx; g0 += TX) {
+      const int g1 = std::min(nx - 1, g0 + TX - 1);
+      const int xb = tx[g0].i0 & ~3;
+      int w = (tx[g1].i1 - xb + 1 + 3) & ~3;
+      if (xb + w > srcnx[m]) w = srcnx[m] - xb;
+      if (w > XS || w < 1 || tx[g1].i1 - xb >= w) return false;
+    }
+    for (int g0 = 0; g0 < ny; g0 += TY) {
+      const int g1 = std::min(ny - 1, g0 + TY - 1);
+      if (ty[g1].i1 - ty[g0].i0 + 1 > YS) return false;
+    }
+    (void)tz;
+  }
+  // z: the steps inside both maps must form one interval, and the planes they touch must be
+  // consecutive in each map (a step may advance the lower plane by at most its own upper plane + 1)
+  const AxisEntry *az = &tab[off[2]], *bz = &tab[off[5]];
+  zlo = -1; zhi = -1;
+  for (int g = 0; g < nz; ++g) {
+    const bool in = az[g].inside && bz[g].inside;
+    if (in) { if (zlo < 0) zlo = g; if (zhi >= 0 && zhi != g) return false; zhi = g + 1; }
+  }
+  if (zlo < 0) return false;
+  for (int m = 0; m < 2; ++m) {
+    const AxisEntry *tz = m ? bz : az;
+    for (int g = zlo; g < zhi; ++g) {
+      if (tz[g].i1 != tz[g].i0 && tz[g].i1 != tz[g].i0 + 1) return false;
+      if (g > zlo && (tz[g].i0 < tz[g - 1].i0 || tz[g].i0 > tz[g - 1].i1 + 1)) return false;
+    }
+  }
+  return true;
+}
+
+// returns 0 launched, 1 not applicable, >1 error
+int k_cc_staged(const DevMap &A, const DevMap &B, int nx, int ny, int nz, const std::vector<AxisEntry> &host_tab,
+                const int off[6], const AxisEntry *d_tab, float thr_f, double *partials, unsigned int *ticket,
+                double *dout) {
+  using namespace staged;
+  constexpr int Y = 4;
+  int zlo, zhi;
+  if (!staged_ok<Y>(host_tab, off, nx, ny, nz, A.nx, B.nx, zlo, zhi)) return 1;
+  Ctx &c = ctx();
+  constexpr int TY = Shape<Y>::TY, YS = Shape<Y>::YS;
+  const size_t smem = sizeof(float) * 2 * (size_t)S * YS * XS + sizeof(unsigned long long) * 4 * S;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VT_CUDA(cudaFuncSetAttribute(cc_staged_kernel<Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int zchunk = 64;
+  const long work = (long)((nx + TX - 1) / TX) * ((ny + TY - 1) / TY) * ((zhi - zlo + zchunk - 1) / zchunk);
+  int grid = (int)std::min<long>(work, (long)c.sm_count * 2);
+  prof_begin(PK_CC);
+  cc_staged_kernel<Y><<<grid, kThreadsStaged, smem, c.stream>>>(A.d, A.nx, A.ny, B.d, B.nx, B.ny, d_tab + off[0],
+                                                                 d_tab + off[1], d_tab + off[2], d_tab + off[3],
+                                                                 d_tab + off[4], d_tab + off[5], nx, ny, nz, zchunk, zlo,
+                                                                 zhi, thr_f, partials, ticket, dout);
+  prof_end(PK_CC);
+  VT_LAUNCHED();
+  return 0;
+}
+
+}  // namespace vt
