@@ -84,7 +84,7 @@ def test_cc_generic_path_matches(oracle, monkeypatch):
 
 def test_cc_staged_ring_path(oracle, monkeypatch):
     """the cp.async.bulk / mbarrier ring variant (forced here on small maps): same samples, sums formed
-    in float per 4 voxels -> 1e-7 on CC; falls back to the direct kernel when its preconditions fail"""
+    in float per 8 voxels -> 1e-7 on CC; falls back to the direct kernel when its preconditions fail"""
     r = np.random.default_rng(11)
     cases = [(OGrid.make((0, 0, 0), (96, 70, 150), 1.0), OGrid.make((0, 0, 0), (96, 70, 150), 1.0)),      # identical
              (OGrid.make((0, 0, 0), (128, 64, 90), 1.0), OGrid.make((0.5, -3.0, 2.25), (132, 60, 96), 1.0)),  # offset

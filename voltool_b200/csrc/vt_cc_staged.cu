@@ -51,6 +51,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
       "r"(parity)
       : "memory");
 }
+// producers are far ahead of the consumers most of the time: back off instead of burning issue slots
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long *bar, unsigned int parity) {
+  unsigned int done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
@@ -77,11 +92,15 @@ __device__ __forceinline__ Box tile_box(const AxisEntry *__restrict__ tx, const 
 
 template <int Y>
 struct Consumer {
-  int x0l, x1l;
+  // unit-stride fast path: every output row/column advances the source index by exactly one
+  int base;      // (first source row - box row 0) * XS + (x0 - box x 0)
+  int base1;     // same for x1 (x1 - x0 is 0 at a clamped edge, else 1)
+  bool unit;     // warp-uniform
+  // generic path re-reads the y table per plane
+  const AxisEntry *ty;
+  int gy0, ny_out, yb, x0l, x1l;
   float xf;
-  int r0l[Y], r1l[Y];
   float yf[Y];
-  unsigned int loadmask;
   int z0, z1;
   float lo[Y], hi[Y];
 };
@@ -90,40 +109,55 @@ template <int Y>
 __device__ __forceinline__ void consumer_init(Consumer<Y> &c, const AxisEntry &ex, const AxisEntry *__restrict__ ty,
                                               int gy0, int ny_out, const Box &b) {
   c.x0l = ex.i0 - b.xb; c.x1l = ex.i1 - b.xb; c.xf = ex.f;
-  c.loadmask = 0u;
+  c.ty = ty; c.gy0 = gy0; c.ny_out = ny_out; c.yb = b.yb;
+  bool rows_unit = true;
+  int first = 0, prev = 0;
 #pragma unroll
   for (int r = 0; r < Y; ++r) {
     const AxisEntry ey = ty[min(gy0 + r, ny_out - 1)];
-    c.r0l[r] = (ey.i0 - b.yb) * XS;
-    c.r1l[r] = (ey.i1 - b.yb) * XS;
     c.yf[r] = ey.f;
-    if (r == 0 || c.r0l[r] != c.r1l[r - 1]) c.loadmask |= 1u << (2 * r);
-    if (c.r1l[r] != c.r0l[r]) c.loadmask |= 1u << (2 * r + 1);
+    if (r == 0) first = ey.i0;
+    else rows_unit = rows_unit && (ey.i0 == prev + 1);
+    rows_unit = rows_unit && (ey.i1 == ey.i0 + 1);
+    prev = ey.i0;
   }
+  c.unit = rows_unit;
+  c.base = (first - b.yb) * XS + c.x0l;
+  c.base1 = (first - b.yb) * XS + c.x1l;
   c.z0 = -1; c.z1 = -1;
 }
 
-// bilinear values of the staged plane for this thread's rows (same expressions as march_plane)
+// bilinear values of the staged plane for this thread's rows: a0 + xf*(a1-a0) per source row,
+// then the y lerp (voxel_value_interpolate, VolumetricData.C:273-287)
 template <int Y>
 __device__ __forceinline__ void consumer_plane(const Consumer<Y> &c, const float *__restrict__ P, float (&out)[Y]) {
+  if (c.unit) {
+    const float *__restrict__ q = P + c.base;
+    const float *__restrict__ q1 = P + c.base1;
+    float xl[Y + 1];
+#pragma unroll
+    for (int r = 0; r <= Y; ++r) {
+      const float v0 = q[r * XS], v1 = q1[r * XS];
+      xl[r] = v0 + c.xf * (v1 - v0);
+    }
+#pragma unroll
+    for (int r = 0; r < Y; ++r) out[r] = xl[r] + c.yf[r] * (xl[r + 1] - xl[r]);
+    return;
+  }
+  int prev_row = -1;
   float prev_xl = 0.f;
 #pragma unroll
   for (int r = 0; r < Y; ++r) {
+    const AxisEntry ey = c.ty[min(c.gy0 + r, c.ny_out - 1)];
+    const int ra = (ey.i0 - c.yb) * XS, rb = (ey.i1 - c.yb) * XS;
     float xa, xb;
-    if ((c.loadmask >> (2 * r)) & 1) {
-      const float v0 = P[c.r0l[r] + c.x0l], v1 = P[c.r0l[r] + c.x1l];
-      xa = v0 + c.xf * (v1 - v0);
-    } else {
-      xa = prev_xl;
-    }
-    if ((c.loadmask >> (2 * r + 1)) & 1) {
-      const float v0 = P[c.r1l[r] + c.x0l], v1 = P[c.r1l[r] + c.x1l];
-      xb = v0 + c.xf * (v1 - v0);
-    } else {
-      xb = xa;
-    }
+    if (ra == prev_row) xa = prev_xl;
+    else { const float v0 = P[ra + c.x0l], v1 = P[ra + c.x1l]; xa = v0 + c.xf * (v1 - v0); }
+    if (rb == ra) xb = xa;
+    else { const float v0 = P[rb + c.x0l], v1 = P[rb + c.x1l]; xb = v0 + c.xf * (v1 - v0); }
+    prev_row = rb;
     prev_xl = xb;
-    out[r] = xa + c.yf[r] * (xb - xa);
+    out[r] = xa + ey.f * (xb - xa);
   }
 }
 
@@ -169,7 +203,7 @@ __device__ __forceinline__ void producer_run(const float *__restrict__ src, int 
   const unsigned int wbytes = (unsigned int)b.wfl * 4u;
   for (int p = p0; p <= p1; ++p) {
     const unsigned int slot = cnt % S, par = ((cnt / S) & 1u) ^ 1u;
-    mbar_wait(&empty[slot], par);
+    mbar_wait_backoff(&empty[slot], par);
     if (lane == 0) mbar_expect_tx(&full[slot], wbytes * (unsigned int)b.nrows);
     __syncwarp();
     float *dst = ring + (size_t)slot * plane_floats;
@@ -180,7 +214,7 @@ __device__ __forceinline__ void producer_run(const float *__restrict__ src, int 
 }
 
 template <int Y>
-__global__ void __launch_bounds__(kThreadsStaged, 2)
+__global__ void __launch_bounds__(kThreadsStaged, (Y > 4 ? 1 : 2))
     cc_staged_kernel(const float *__restrict__ A, int anx, int any, const float *__restrict__ B, int bnx, int bny,
                      const AxisEntry *__restrict__ tAx, const AxisEntry *__restrict__ tAy,
                      const AxisEntry *__restrict__ tAz, const AxisEntry *__restrict__ tBx,
@@ -206,6 +240,7 @@ __global__ void __launch_bounds__(kThreadsStaged, 2)
   __syncthreads();
 
   double acc[6] = {0, 0, 0, 0, 0, 0};
+  long long nvox = 0;
   unsigned int cntA = 0, cntB = 0;
   const int xtiles = (nx + TX - 1) / TX, ytiles = (ny + TY - 1) / TY;
   const int zchunks = (zhi - zlo + zchunk - 1) / zchunk;
@@ -253,10 +288,11 @@ __global__ void __launch_bounds__(kThreadsStaged, 2)
           cnt += take ? 1 : 0;
         }
         acc[0] += (double)fA; acc[1] += (double)fB; acc[2] += (double)fAA; acc[3] += (double)fBB; acc[4] += (double)fAB;
-        acc[5] += (double)cnt;
+        nvox += cnt;
       }
     }
   }
+  acc[5] = (double)nvox;
   block_sum<6>(acc, sm);
   grid_finish<6>(acc, partials, ticket, out, sm);
 }
@@ -307,25 +343,20 @@ static bool staged_ok(const std::vector<AxisEntry> &tab, const int off[6], int n
   return true;
 }
 
-// returns 0 launched, 1 not applicable, >1 error
-int k_cc_staged(const DevMap &A, const DevMap &B, int nx, int ny, int nz, const std::vector<AxisEntry> &host_tab,
-                const int off[6], const AxisEntry *d_tab, float thr_f, double *partials, unsigned int *ticket,
-                double *dout) {
+template <int Y>
+static int launch_staged(const DevMap &A, const DevMap &B, int nx, int ny, int nz, const std::vector<AxisEntry> &host_tab,
+                         const int off[6], const AxisEntry *d_tab, float thr_f, double *partials, unsigned int *ticket,
+                         double *dout) {
   using namespace staged;
-  constexpr int Y = 4;
   int zlo, zhi;
   if (!staged_ok<Y>(host_tab, off, nx, ny, nz, A.nx, B.nx, zlo, zhi)) return 1;
   Ctx &c = ctx();
   constexpr int TY = Shape<Y>::TY, YS = Shape<Y>::YS;
   const size_t smem = sizeof(float) * 2 * (size_t)S * YS * XS + sizeof(unsigned long long) * 4 * S;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VT_CUDA(cudaFuncSetAttribute(cc_staged_kernel<Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  VT_CUDA(cudaFuncSetAttribute(cc_staged_kernel<Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int zchunk = 64;
   const long work = (long)((nx + TX - 1) / TX) * ((ny + TY - 1) / TY) * ((zhi - zlo + zchunk - 1) / zchunk);
-  int grid = (int)std::min<long>(work, (long)c.sm_count * 2);
+  int grid = (int)std::min<long>(work, (long)c.sm_count * (Y > 4 ? 1 : 2));
   prof_begin(PK_CC);
   cc_staged_kernel<Y><<<grid, kThreadsStaged, smem, c.stream>>>(A.d, A.nx, A.ny, B.d, B.nx, B.ny, d_tab + off[0],
                                                                  d_tab + off[1], d_tab + off[2], d_tab + off[3],
@@ -334,6 +365,15 @@ int k_cc_staged(const DevMap &A, const DevMap &B, int nx, int ny, int nz, const 
   prof_end(PK_CC);
   VT_LAUNCHED();
   return 0;
+}
+
+// returns 0 launched, 1 not applicable, >1 error
+int k_cc_staged(const DevMap &A, const DevMap &B, int nx, int ny, int nz, const std::vector<AxisEntry> &host_tab,
+                const int off[6], const AxisEntry *d_tab, float thr_f, double *partials, unsigned int *ticket,
+                double *dout) {
+  const char *e = getenv("VOLTOOL_CC_Y");
+  if (e && atoi(e) == 8) return launch_staged<8>(A, B, nx, ny, nz, host_tab, off, d_tab, thr_f, partials, ticket, dout);
+  return launch_staged<4>(A, B, nx, ny, nz, host_tab, off, d_tab, thr_f, partials, ticket, dout);
 }
 
 }  // namespace vt
