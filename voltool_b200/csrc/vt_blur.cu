@@ -7,6 +7,8 @@
 // Pass structure: the x pass stages each row segment (+halo) in shared memory; the y and z
 // passes march a register window along the filtered axis so each input element is read from
 // L2/HBM once per pass.
+#include <cstdlib>
+
 #include "vt_device.cuh"
 
 namespace vt {
@@ -74,6 +76,170 @@ __global__ void __launch_bounds__(256) blur_axis_kernel(const float *__restrict_
   }
 }
 
+// ---- compile-time radius: taps become immediate constant-bank operands, every loop is static,
+// and each thread produces a run of outputs from one sliding window of inputs (each input is
+// loaded once per thread instead of once per tap).  Tap order per output is unchanged.
+template <int R, int XB>
+__global__ void __launch_bounds__(256) blur_x_fixed_kernel(const float *__restrict__ in, float *__restrict__ out, int nx,
+                                                           long rows, int rows_per_block) {
+  extern __shared__ __align__(16) float srows[];  // rows_per_block x pitch
+  const int segs = (nx + XB - 1) / XB;
+  const int pitch = ((segs * XB + 2 * R + 3) & ~3) + 4;
+  for (long r0 = (long)blockIdx.x * rows_per_block; r0 < rows; r0 += (long)gridDim.x * rows_per_block) {
+    const int nr = (int)((rows - r0) < rows_per_block ? (rows - r0) : rows_per_block);
+    for (int rr = 0; rr < nr; ++rr) {
+      const float *src = in + (r0 + rr) * nx;
+      float *d = srows + rr * pitch;
+      for (int c = threadIdx.x; c < pitch; c += blockDim.x) {
+        int j = c - R;
+        j = j < 0 ? 0 : (j > nx - 1 ? nx - 1 : j);
+        d[c] = __ldcs(src + j);
+      }
+    }
+    __syncthreads();
+    // consecutive threads take consecutive XB-wide segments of one row: with XB = 4 every float4
+    // read below is a conflict-free 512-byte warp access
+    for (int t = threadIdx.x; t < nr * segs; t += blockDim.x) {
+      const int rr = t / segs, sg = t - rr * segs;
+      const float *w = srows + rr * pitch + sg * XB;  // window: outputs sg*XB.. need w[0 .. XB+2R)
+      float v[XB + 2 * R + 3];
+#pragma unroll
+      for (int q = 0; q < (XB + 2 * R + 3) / 4; ++q) {
+        const float4 f = *reinterpret_cast<const float4 *>(w + 4 * q);
+        v[4 * q + 0] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+      }
+      float acc[XB];
+#pragma unroll
+      for (int s = 0; s < XB; ++s) {
+        float a = 0.0f;
+#pragma unroll
+        for (int k = 0; k <= 2 * R; ++k) a = __fmaf_rn(c_taps[k], v[s + k], a);
+        acc[s] = a;
+      }
+      float *o = out + (r0 + rr) * nx + sg * XB;
+      if (XB == 4 && (nx & 3) == 0) {
+        *reinterpret_cast<float4 *>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      } else {
+#pragma unroll
+        for (int s = 0; s < XB; ++s)
+          if (sg * XB + s < nx) o[s] = acc[s];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// x pass without shared memory: a thread produces 4 consecutive outputs from a window of aligned
+// float4 loads (consecutive lanes -> consecutive 16-byte pieces; the overlap between neighbouring
+// windows is served by L1).  Segments whose window would cross a row end take clamped scalar loads.
+template <int R>
+__global__ void __launch_bounds__(256) blur_x_direct_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                            int nx, long rows) {
+  constexpr int OFF = (4 - (R & 3)) & 3;            // (x0 - R) - first aligned x, for x0 % 4 == 0
+  constexpr int NQ = (OFF + 4 + 2 * R + 3) / 4;      // float4 loads per window
+  const int segs = (nx + 3) >> 2;
+  const long work = rows * segs;
+  const long step = (long)gridDim.x * blockDim.x;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += step) {
+    const long row = t / segs;
+    const int sg = (int)(t - row * segs), x0 = sg * 4;
+    const float *src = in + row * nx;
+    const int first = x0 - R - OFF;
+    float v[4 * NQ];
+    if (first >= 0 && first + 4 * NQ <= nx) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(src + first) + q);
+        v[4 * q + 0] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4 * NQ; ++i) {
+        int j = first + i;
+        j = j < 0 ? 0 : (j > nx - 1 ? nx - 1 : j);
+        v[i] = __ldg(src + j);
+      }
+    }
+    float acc[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      float a = 0.0f;
+#pragma unroll
+      for (int k = 0; k <= 2 * R; ++k) a = __fmaf_rn(c_taps[k], v[OFF + s + k], a);
+      acc[s] = a;
+    }
+    float *o = out + row * nx + x0;
+    if (x0 + 4 <= nx) *reinterpret_cast<float4 *>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        if (x0 + s < nx) o[s] = acc[s];
+  }
+}
+
+template <int R, int SEG>
+__global__ void __launch_bounds__(256) blur_axis_fixed_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                              int n_axis, long stride, long inner, long outer) {
+  const long lines = inner * outer;
+  const int nseg = (n_axis + SEG - 1) / SEG;
+  const long work = lines * nseg;
+  const long step = (long)gridDim.x * blockDim.x;
+  for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < work; w += step) {
+    const long line = w % lines;
+    const int seg = (int)(w / lines);
+    const long o = line / inner, i = line - o * inner;
+    const float *src = in + o * (n_axis * stride) + i;
+    float *dst = out + o * (n_axis * stride) + i;
+    const int a0 = seg * SEG;
+    float acc[SEG];
+#pragma unroll
+    for (int s = 0; s < SEG; ++s) acc[s] = 0.0f;
+#pragma unroll
+    for (int t = 0; t < SEG + 2 * R; ++t) {
+      int j = a0 - R + t;
+      j = j < 0 ? 0 : (j > n_axis - 1 ? n_axis - 1 : j);
+      const float v = __ldg(src + (long)j * stride);
+#pragma unroll
+      for (int s = 0; s < SEG; ++s)
+        if (t - s >= 0 && t - s <= 2 * R) acc[s] = __fmaf_rn(c_taps[t - s], v, acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < SEG; ++s)
+      if (a0 + s < n_axis) dst[(long)(a0 + s) * stride] = acc[s];
+  }
+}
+
+template <int R>
+static int blur_fixed(const float *src, float *dst, float *tmp, int nx, int ny, int nz) {
+  Ctx &c = ctx();
+  constexpr int XB = 4, SEG = 16;
+  const long rows = (long)ny * nz;
+  const int segs = (nx + XB - 1) / XB;
+  const int pitch = ((segs * XB + 2 * R + 3) & ~3) + 4;
+  int rpb = 1024 / (segs > 0 ? segs : 1);  // ~4 segments per thread per batch
+  if (rpb < 1) rpb = 1;
+  if (rpb > 16) rpb = 16;
+  size_t smem = sizeof(float) * (size_t)rpb * pitch;
+  while (smem > 96 * 1024 && rpb > 1) { rpb /= 2; smem = sizeof(float) * (size_t)rpb * pitch; }
+  if (smem > 200 * 1024) return 1;  // absurdly wide rows: caller falls back
+  if (smem > 48 * 1024)
+    VT_CUDA(cudaFuncSetAttribute(blur_x_fixed_kernel<R, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long blocks = (rows + rpb - 1) / rpb;
+  int grid = (int)(blocks < (long)c.sm_count * 8 ? blocks : (long)c.sm_count * 8);
+  if ((nx & 3) == 0) {  // rows 16-byte aligned: direct float4 windows
+    blur_x_direct_kernel<R><<<c.sm_count * 8, 256, 0, c.stream>>>(src, dst, nx, rows);
+  } else {
+    blur_x_fixed_kernel<R, XB><<<grid, 256, smem, c.stream>>>(src, dst, nx, rows, rpb);
+  }
+  VT_LAUNCHED();
+  const int g2 = c.sm_count * 8;
+  blur_axis_fixed_kernel<R, SEG><<<g2, 256, 0, c.stream>>>(dst, tmp, ny, (long)nx, (long)nx, (long)nz);
+  VT_LAUNCHED();
+  blur_axis_fixed_kernel<R, SEG><<<g2, 256, 0, c.stream>>>(tmp, dst, nz, (long)nx * ny, (long)nx * ny, 1L);
+  VT_LAUNCHED();
+  return 0;
+}
+
 int k_blur(const float *src, float *dst, float *tmp, int nx, int ny, int nz, const float *w, int R) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
@@ -84,6 +250,25 @@ int k_blur(const float *src, float *dst, float *tmp, int nx, int ny, int nz, con
   if (grid < 1) grid = 1;
   // x: src -> dst ; y: dst -> tmp ; z: tmp -> dst
   prof_begin(PK_BLUR);
+  if (!getenv("VOLTOOL_BLUR_GENERIC")) {
+    int rc = 1;
+    switch (R) {
+      case 1: rc = blur_fixed<1>(src, dst, tmp, nx, ny, nz); break;
+      case 2: rc = blur_fixed<2>(src, dst, tmp, nx, ny, nz); break;
+      case 3: rc = blur_fixed<3>(src, dst, tmp, nx, ny, nz); break;
+      case 4: rc = blur_fixed<4>(src, dst, tmp, nx, ny, nz); break;
+      case 5: rc = blur_fixed<5>(src, dst, tmp, nx, ny, nz); break;
+      case 6: rc = blur_fixed<6>(src, dst, tmp, nx, ny, nz); break;
+      case 7: rc = blur_fixed<7>(src, dst, tmp, nx, ny, nz); break;
+      case 8: rc = blur_fixed<8>(src, dst, tmp, nx, ny, nz); break;
+      case 9: rc = blur_fixed<9>(src, dst, tmp, nx, ny, nz); break;
+      case 10: rc = blur_fixed<10>(src, dst, tmp, nx, ny, nz); break;
+      case 12: rc = blur_fixed<12>(src, dst, tmp, nx, ny, nz); break;
+      default: break;
+    }
+    if (rc == 0) { prof_end(PK_BLUR); return 0; }
+    if (rc > 1) return rc;
+  }
   blur_x_kernel<<<grid, 256, sizeof(float) * (nx + 2 * R), c.stream>>>(src, dst, nx, rows, R);
   VT_LAUNCHED();
   const int g2 = c.sm_count * 8;
