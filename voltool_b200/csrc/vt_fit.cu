@@ -70,6 +70,8 @@ int sim_to_map(const float *pos, const float *radii, long natoms, int quality, f
   if (!rc) rc = dev_alloc((void **)&pb.d_geom, sizeof(PoseGeom));
   if (!rc) rc = dev_alloc((void **)&pb.d_totals, sizeof(int) * 4);
   if (!rc) rc = dev_alloc((void **)&pb.d_grid, sizeof(float) * (size_t)cells);
+  pb.tiles_cap = ((nv[0] + kTX - 1) / kTX) * ((nv[1] + kTY - 1) / kTY) * ((nv[2] + kTZ - 1) / kTZ);
+  if (!rc) rc = dev_alloc((void **)&pb.d_bitmap, sizeof(unsigned int) * (size_t)pb.tiles_cap * ((as.ngroups + 31) / 32));
   const float com0[3] = {0.f, 0.f, 0.f};
   if (!rc) rc = batch_prepare(as, pb, 1, nullptr, com0, 1, nullptr);
   if (!rc) rc = batch_splat(as, pb, 1);

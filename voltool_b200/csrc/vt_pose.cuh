@@ -68,6 +68,8 @@ struct PoseBatch {
   unsigned int *d_bbox = nullptr;
   PoseGeom *d_geom = nullptr;
   int *d_totals = nullptr;  // [0] tiles, [1] cc items
+  unsigned int *d_bitmap = nullptr;  // [B][tiles_cap][ceil(ngroups/32)]: groups that can reach a tile
+  int tiles_cap = 0;
   float *d_grid = nullptr;
   geom::AxisEntry *d_tab = nullptr;  // [B][6][cap_o]
   double *d_part = nullptr;          // [B][cap_items][6]

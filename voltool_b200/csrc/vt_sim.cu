@@ -197,6 +197,11 @@ int batch_create(const AtomSet &as, const vt_grid *target, int B, PoseBatch &pb)
   if (dev_alloc((void **)&pb.d_bbox, sizeof(unsigned int) * 6 * B)) return 2;
   if (dev_alloc((void **)&pb.d_geom, sizeof(PoseGeom) * B)) return 2;
   if (dev_alloc((void **)&pb.d_totals, sizeof(int) * 4)) return 2;
+  {
+    const int tn = (pb.cap_n + kTX - 1) / kTX, tm = (pb.cap_n + kTY - 1) / kTY, tk = (pb.cap_n + kTZ - 1) / kTZ;
+    pb.tiles_cap = tn * tm * tk;
+    if (dev_alloc((void **)&pb.d_bitmap, sizeof(unsigned int) * (size_t)B * pb.tiles_cap * ((as.ngroups + 31) / 32))) return 2;
+  }
   if (dev_alloc((void **)&pb.d_grid, sizeof(float) * (size_t)B * pb.cap_grid)) return 2;
   if (dev_alloc((void **)&pb.d_prep, sizeof(PrepPose) * B)) return 2;
   if (target) {
@@ -207,7 +212,7 @@ int batch_create(const AtomSet &as, const vt_grid *target, int B, PoseBatch &pb)
 }
 
 void batch_destroy(PoseBatch &pb) {
-  dev_free(pb.d_tpos); dev_free(pb.d_tgroup); dev_free(pb.d_bbox); dev_free(pb.d_geom); dev_free(pb.d_totals);
+  dev_free(pb.d_tpos); dev_free(pb.d_tgroup); dev_free(pb.d_bbox); dev_free(pb.d_geom); dev_free(pb.d_totals); dev_free(pb.d_bitmap);
   dev_free(pb.d_grid); dev_free(pb.d_prep); dev_free(pb.d_tab); dev_free(pb.d_part);
   pb = PoseBatch();
 }
@@ -413,21 +418,65 @@ __device__ __forceinline__ int find_pose(const PoseGeom *__restrict__ geo, int n
   return lo;
 }
 
-constexpr int kWRec = 20;  // floats per warp-staged atom: Ex[8] | dy^2[8] | dz^2[4]
+constexpr int kWRec = 20;     // floats per warp-staged atom: Ex[8] | dy^2[8] | dz^2[4]
+constexpr int kGChunk = 1024; // groups expanded from the bitmap at a time (32 words, one warp)
+constexpr int kWGroups = 32;  // groups a warp gathers per batch
+constexpr int kWList = kWGroups * 32;  // per-warp gathered atoms per batch
+
+// Which groups can touch which tile: thread per (pose, group) marks the tiles its bounding sphere
+// reaches in a per-tile bitmap (atomicOr: the result does not depend on the order).  The splat
+// kernel then walks set bits in index order, so its accumulation order stays deterministic.
+__global__ void __launch_bounds__(256) pose_bin_kernel(const PoseGeom *__restrict__ geo, int ngroups,
+                                                       const float4 *__restrict__ tgroup_all, float gs, float invgs,
+                                                       unsigned int *__restrict__ bitmap, int tiles_cap, int nwords) {
+  const int p = blockIdx.y;
+  const PoseGeom &G = geo[p];
+  const int ntx = G.tiles[0], nty = G.tiles[1], ntz = G.tiles[2];
+  if (ntx == 0) return;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+    const float4 c = tgroup_all[(size_t)p * ngroups + g];
+    const float rx = (c.x - G.org[0]) * invgs, ry = (c.y - G.org[1]) * invgs, rz = (c.z - G.org[2]) * invgs;
+    const float rr = c.w * invgs + 2.0f;  // reach in voxels + slack; the exact test below decides
+    const int tx0 = max(0, (int)floorf((rx - rr) / kTX) - 1), tx1 = min(ntx - 1, (int)floorf((rx + rr) / kTX) + 1);
+    const int ty0 = max(0, (int)floorf((ry - rr) / kTY) - 1), ty1 = min(nty - 1, (int)floorf((ry + rr) / kTY) + 1);
+    const int tz0 = max(0, (int)floorf((rz - rr) / kTZ) - 1), tz1 = min(ntz - 1, (int)floorf((rz + rr) / kTZ) + 1);
+    for (int tz = tz0; tz <= tz1; ++tz)
+      for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) {
+          // tile box in cartesian space with one voxel of slack for the integer truncations
+          const int x0 = tx * kTX, y0 = ty * kTY, z0 = tz * kTZ;
+          const float bx0 = G.org[0] + (x0 - 1) * gs, bx1 = G.org[0] + (x0 + kTX) * gs;
+          const float by0 = G.org[1] + (y0 - 1) * gs, by1 = G.org[1] + (y0 + kTY) * gs;
+          const float bz0 = G.org[2] + (z0 - 1) * gs, bz1 = G.org[2] + (z0 + kTZ) * gs;
+          const float dx = fmaxf(fmaxf(bx0 - c.x, 0.0f), c.x - bx1);
+          const float dy = fmaxf(fmaxf(by0 - c.y, 0.0f), c.y - by1);
+          const float dz = fmaxf(fmaxf(bz0 - c.z, 0.0f), c.z - bz1);
+          if (dx * dx + dy * dy + dz * dz <= c.w * c.w) {
+            const int tile = (tz * nty + ty) * ntx + tx;
+            atomicOr(&bitmap[((size_t)p * tiles_cap + tile) * nwords + (g >> 5)], 1u << (g & 31));
+          }
+        }
+  }
+}
 
 __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
                                                        int npose, int natoms, int ngroups,
                                                        const float4 *__restrict__ tpos_all,
-                                                       const float4 *__restrict__ tgroup_all,
+                                                       const unsigned int *__restrict__ bitmap, int tiles_cap, int nwords,
                                                        const float4 *__restrict__ cst, float gs, float invgs,
                                                        float *__restrict__ grid_all, long cap_grid) {
-  __shared__ __align__(16) float s_rec[8][32 * kWRec];  // warp-private staged records
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  float(*s_rec)[32 * kWRec] = reinterpret_cast<float(*)[32 * kWRec]>(s_dyn);          // warp-private staged records
+  unsigned short(*s_wid)[kWList] = reinterpret_cast<unsigned short(*)[kWList]>(s_dyn + sizeof(float) * 8 * 32 * kWRec);
+  unsigned char(*s_wm)[kWList] = reinterpret_cast<unsigned char(*)[kWList]>(s_dyn + sizeof(float) * 8 * 32 * kWRec +
+                                                                            sizeof(unsigned short) * 8 * kWList);
+  // s_wid: atoms gathered by warp w whose box meets this tile, as (index in s_glist) << 5 | lane;
+  // s_wm: which of the 8 warp regions they meet
   __shared__ float s_ar[8][32], s_rl2[8][32];           // arinv, (gausslim*sigma)^2 per staged atom
   __shared__ int s_pend[8][64];                         // warp-private pending ids
-  __shared__ int s_ids[kMaxIds];                        // atoms whose box meets this tile
-  __shared__ unsigned char s_mask[kMaxIds];             // ... and which of the 8 warp regions they meet
-  __shared__ int s_cells[256];
-  __shared__ int s_wcnt[8];
+  __shared__ int s_wn[8];
+  __shared__ unsigned short s_glist[kGChunk];           // groups (offsets inside the chunk) that can reach the tile
+  __shared__ int s_scan[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned int lt = (1u << lane) - 1u;
   const int wx = warp & 1, wy = (warp >> 1) & 1, wz = warp >> 2;
@@ -442,11 +491,7 @@ __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restric
     const int nv0 = G.nv[0], nv1 = G.nv[1], nv2 = G.nv[2];
     const float ox = G.org[0], oy = G.org[1], oz = G.org[2];
     const float4 *__restrict__ tpos = tpos_all + (size_t)p * natoms;
-    const float4 *__restrict__ tgroup = tgroup_all + (size_t)p * ngroups;
-    // tile box in cartesian space with one voxel of slack for the integer truncations
-    const float bx0 = ox + (x0 - 1) * gs, bx1 = ox + (x0 + kTX) * gs;
-    const float by0 = oy + (y0 - 1) * gs, by1 = oy + (y0 + kTY) * gs;
-    const float bz0 = oz + (z0 - 1) * gs, bz1 = oz + (z0 + kTZ) * gs;
+    const unsigned int *__restrict__ bits = bitmap + ((size_t)p * tiles_cap + local) * nwords;
     // this warp's 8x8x4 region and this thread's column inside it
     const int X0 = x0 + wx * 8, Y0 = y0 + wy * 8, Z0 = z0 + wz * 4;
     const int ly = lane & 7, lz = lane >> 3;
@@ -454,10 +499,8 @@ __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restric
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
-    int nids = 0;
 
-    // ---- phase 2 (warp-independent): filter the tile list by region, stage 32 atoms at a time
-    //      (lane per atom), accumulate.  No block barrier in here.
+    // ---- phase 2 (warp-independent): stage 32 atoms (lane per atom), accumulate ----
     auto process = [&](int n) {
       float *rec = s_rec[warp];
       if (lane < n) {
@@ -518,55 +561,68 @@ __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restric
       __syncwarp();
     };
 
-    auto flush = [&](int count) {
+    // every warp walks the 8 gathered lists in the same order, keeping the atoms whose box meets
+    // its own region
+    auto drain = [&](int gbase) {
       int have = 0;
-      for (int b0 = 0; b0 < count; b0 += 32) {
-        const int i = b0 + lane;
-        const bool mine = i < count && ((s_mask[i] >> warp) & 1);
-        const unsigned int bal = __ballot_sync(0xffffffffu, mine);
-        if (bal == 0u) continue;
-        if (mine) s_pend[warp][have + __popc(bal & lt)] = s_ids[i];
-        have += __popc(bal);
-        __syncwarp();
-        if (have >= 32) {
-          process(32);
-          const int rest = have - 32;
-          const int keep = lane < rest ? s_pend[warp][32 + lane] : 0;
+      for (int l = 0; l < 8; ++l) {
+        const int count = s_wn[l];
+        for (int b0 = 0; b0 < count; b0 += 32) {
+          const int i = b0 + lane;
+          const bool mine = i < count && ((s_wm[l][i] >> warp) & 1);
+          const unsigned int bal = __ballot_sync(0xffffffffu, mine);
+          if (bal == 0u) continue;
+          if (mine) {
+            const int e = s_wid[l][i];
+            s_pend[warp][have + __popc(bal & lt)] = (gbase + (int)s_glist[e >> 5]) * 32 + (e & 31);
+          }
+          have += __popc(bal);
           __syncwarp();
-          if (lane < rest) s_pend[warp][lane] = keep;
-          have = rest;
-          __syncwarp();
+          if (have >= 32) {
+            process(32);
+            const int rest = have - 32;
+            const int keep = lane < rest ? s_pend[warp][32 + lane] : 0;
+            __syncwarp();
+            if (lane < rest) s_pend[warp][lane] = keep;
+            have = rest;
+            __syncwarp();
+          }
         }
       }
       if (have > 0) process(have);
     };
 
-    // ---- phase 1 (block-cooperative): which atoms meet this tile ----
-    for (int g0 = 0; g0 < ngroups; g0 += 256) {
-      // cull 256 groups: thread per group, bounding sphere vs tile box
-      const int g = g0 + tid;
-      bool hit = false;
-      if (g < ngroups) {
-        const float4 c = tgroup[g];
-        const float dx = fmaxf(fmaxf(bx0 - c.x, 0.0f), c.x - bx1);
-        const float dy = fmaxf(fmaxf(by0 - c.y, 0.0f), c.y - by1);
-        const float dz = fmaxf(fmaxf(bz0 - c.z, 0.0f), c.z - bz1);
-        hit = dx * dx + dy * dy + dz * dz <= c.w * c.w;
-      }
-      const unsigned int bal = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0) s_wcnt[warp] = __popc(bal);
-      __syncthreads();
-      int off = 0, nc = 0;
+    // ---- phase 1: expand the tile's group bitmap, gather atoms (warp per group) ----
+    for (int w0 = 0; w0 < nwords; w0 += kGChunk / 32) {
+      // 32 words -> ordered list of set bits (warp 0)
+      if (warp == 0) {
+        unsigned int word = (w0 + lane < nwords) ? bits[w0 + lane] : 0u;
+        const int pc = __popc(word);
+        int incl = pc;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) { const int cw = s_wcnt[w]; if (w < warp) off += cw; nc += cw; }
-      if (hit) s_cells[off + __popc(bal & lt)] = g;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[0] = incl;
+        int off = incl - pc;
+        while (word) {
+          const int bit = __ffs(word) - 1;
+          word &= word - 1;
+          s_glist[off++] = (unsigned short)(lane * 32 + bit);
+        }
+      }
       __syncthreads();
-      // exact atom test: warp per surviving group (the reference's truncated integer box)
-      for (int c0 = 0; c0 < nc; c0 += 8) {
-        bool take = false;
-        int id = -1, mask = 0;
-        if (c0 + warp < nc) {
-          id = s_cells[c0 + warp] * 32 + lane;
+      const int nhit = s_scan[0];
+      for (int b0 = 0; b0 < nhit; b0 += 8 * kWGroups) {
+        // each warp tests the atoms of up to kWGroups groups with the reference's truncated integer box
+        int cnt = 0;
+        for (int j = 0; j < kWGroups; ++j) {
+          const int gi = b0 + warp + 8 * j;
+          if (gi >= nhit) break;
+          const int id = (w0 * 32 + (int)s_glist[gi]) * 32 + lane;
+          bool take = false;
+          int mask = 0;
           if (id < natoms) {
             const float4 a4 = tpos[id];
             const float rl = cst[id].z;
@@ -589,28 +645,20 @@ __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restric
                 if (((mx >> (w & 1)) & 1) && ((my >> ((w >> 1) & 1)) & 1) && ((mz >> (w >> 2)) & 1)) mask |= 1 << w;
             }
           }
+          const unsigned int b2 = __ballot_sync(0xffffffffu, take);
+          if (take) {
+            const int slot = cnt + __popc(b2 & lt);
+            s_wid[warp][slot] = (unsigned short)((gi << 5) | lane);
+            s_wm[warp][slot] = (unsigned char)mask;
+          }
+          cnt += __popc(b2);
         }
-        const unsigned int b2 = __ballot_sync(0xffffffffu, take);
-        if (lane == 0) s_wcnt[warp] = __popc(b2);
+        if (lane == 0) s_wn[warp] = cnt;
         __syncthreads();
-        int o2 = nids, add = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { const int cw = s_wcnt[w]; if (w < warp) o2 += cw; add += cw; }
-        if (take) {
-          const int slot = o2 + __popc(b2 & lt);
-          s_ids[slot] = id;
-          s_mask[slot] = (unsigned char)mask;
-        }
-        nids += add;
+        drain(w0 * 32);
         __syncthreads();
-        if (nids > kMaxIds - 256) {
-          flush(nids);
-          nids = 0;
-          __syncthreads();
-        }
       }
     }
-    if (nids > 0) flush(nids);
 
     // ---- every voxel of the tile written exactly once ----
     const int Y = Y0 + ly, Z = Z0 + lz;
@@ -620,17 +668,31 @@ __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restric
       for (int k = 0; k < 8; ++k)
         if (X0 + k < nv0) row[X0 + k] = acc[k];
     }
-    __syncthreads();
   }
 }
 
 int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
+  const int nwords = (as.ngroups + 31) / 32;
+  prof_begin(PK_SETUP);
+  VT_CUDA(cudaMemsetAsync(pb.d_bitmap, 0, sizeof(unsigned int) * (size_t)npose * pb.tiles_cap * nwords, c.stream));
+  int gx = (as.ngroups + 255) / 256;
+  if (gx > 32) gx = 32;
+  pose_bin_kernel<<<dim3(gx, npose), 256, 0, c.stream>>>(pb.d_geom, as.ngroups, pb.d_tgroup, as.prm.gs, as.prm.invgs,
+                                                          pb.d_bitmap, pb.tiles_cap, nwords);
+  prof_end(PK_SETUP);
+  VT_LAUNCHED();
   const int grid = c.sm_count * 3 * 4;  // persistent: 3 resident CTAs per SM, 4 rounds for uneven tiles
   prof_begin(PK_SPLAT);
-  splat_kernel<<<grid, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, as.ngroups, pb.d_tpos, pb.d_tgroup,
-                                           as.d_const, as.prm.gs, as.prm.invgs, pb.d_grid, pb.cap_grid);
+  const size_t smem = sizeof(float) * 8 * 32 * kWRec + (sizeof(unsigned short) + 1) * 8 * kWList;
+  static bool attr = false;
+  if (!attr) {
+    VT_CUDA(cudaFuncSetAttribute(splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  splat_kernel<<<grid, 256, smem, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, as.ngroups, pb.d_tpos, pb.d_bitmap,
+                                           pb.tiles_cap, nwords, as.d_const, as.prm.gs, as.prm.invgs, pb.d_grid, pb.cap_grid);
   prof_end(PK_SPLAT);
   VT_LAUNCHED();
   return 0;
