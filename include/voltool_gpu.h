@@ -101,6 +101,9 @@ int vt_mean(vt_map *m, float *mean);                                  /* ::mean 
 int vt_sigma(vt_map *m, float *sigma);                                /* ::sigma :1095-1100 */
 int vt_vol_com(const vt_map *m, float com[3]);                        /* vol_com, Voltool.C:229-247 */
 int vt_histogram(vt_map *m, int nbins, long *bins, float *midpts);    /* histogram, Voltool.C:443-461 */
+/* metadata only: translate / rigidly transform the map frame (column-major 4x4, translation in m[12..14]) */
+int vt_vol_moveto(vt_map *m, const float com[3], const float pos[3]); /* vol_moveto, Voltool.C:379-391 */
+int vt_vol_move(vt_map *m, const float mat[16]);                       /* vol_move, Voltool.C:399-438 */
 
 /* ---------------------------------------------------------------- resizing ops (replace data) */
 int vt_pad(vt_map *m, int padxm, int padxp, int padym, int padyp, int padzm, int padzp); /* ::pad :542-609; trim = pad(-t) TclVoltool.C:1185 */

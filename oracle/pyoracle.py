@@ -117,6 +117,8 @@ class Oracle:
         L.vo_sigma.argtypes = [C.POINTER(Grid), c_float_p, C.POINTER(Cache)]
         L.vo_sigma.restype = C.c_float
         L.vo_vol_com.argtypes = [C.POINTER(Grid), c_float_p, c_float_p]
+        L.vo_vol_moveto.argtypes = [C.POINTER(Grid), c_float_p, c_float_p]
+        L.vo_vol_move.argtypes = [C.POINTER(Grid), c_float_p]
         L.vo_histogram.argtypes = [C.POINTER(Grid), c_float_p, C.POINTER(Cache), C.c_int, C.POINTER(C.c_long), c_float_p]
         L.vo_pad.argtypes = [C.POINTER(Grid), c_float_p, C.POINTER(c_float_p)] + [C.c_int] * 6
         L.vo_crop.argtypes = [C.POINTER(Grid), c_float_p, C.POINTER(c_float_p)] + [C.c_double] * 6
@@ -208,6 +210,16 @@ class Oracle:
         com = np.zeros(3, np.float32)
         self.lib.vo_vol_com(C.byref(g), fp(d), fp(com))
         return com
+
+    def vol_moveto(self, g, com, pos):
+        g2, com, pos = g.copy(), f32(com), f32(pos)
+        self.lib.vo_vol_moveto(C.byref(g2), fp(com), fp(pos))
+        return g2
+
+    def vol_move(self, g, mat):
+        g2, mat = g.copy(), f32(mat)
+        self.lib.vo_vol_move(C.byref(g2), fp(mat))
+        return g2
 
     def histogram(self, g, d, cache, nbins):
         d = f32(d)
@@ -363,6 +375,8 @@ class Ref(Oracle):
         L.ref_vol_sigma.argtypes = [C.c_void_p]
         L.ref_vol_sigma.restype = C.c_float
         L.ref_vol_com.argtypes = [C.c_void_p, c_float_p]
+        L.ref_vol_moveto.argtypes = [C.c_void_p, c_float_p, c_float_p]
+        L.ref_vol_move.argtypes = [C.c_void_p, c_float_p]
         L.ref_vol_histogram.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_long), c_float_p]
         L.ref_voxel_coord.argtypes = [C.c_void_p, C.c_long, c_float_p]
         L.ref_voxel_coord_int.argtypes = [C.c_void_p, C.c_int, c_float_p]
@@ -432,6 +446,16 @@ class Ref(Oracle):
             com = np.zeros(3, np.float32)
             self.ref.lib.ref_vol_com(self.h, fp(com))
             return com
+
+        def moveto(self, com, pos):
+            com, pos = f32(com), f32(pos)
+            self.ref.lib.ref_vol_moveto(self.h, fp(com), fp(pos))
+            return self
+
+        def move(self, mat):
+            mat = f32(mat)
+            self.ref.lib.ref_vol_move(self.h, fp(mat))
+            return self
 
         def histogram(self, nbins):
             bins = (C.c_long * nbins)()

@@ -165,6 +165,8 @@ void ref_vol_datarange(void *h, float *mn, float *mx) { ((VolumetricData *)h)->d
 float ref_vol_mean(void *h) { return ((VolumetricData *)h)->mean(); }
 float ref_vol_sigma(void *h) { return ((VolumetricData *)h)->sigma(); }
 void ref_vol_com(void *h, float *com) { vol_com((VolumetricData *)h, com); }
+void ref_vol_moveto(void *h, float *com, float *pos) { vol_moveto((VolumetricData *)h, com, pos); }
+void ref_vol_move(void *h, float *mat) { vol_move((VolumetricData *)h, mat); }
 void ref_vol_histogram(void *h, int nbins, long *bins, float *midpts) {
   /* one spare slot: the reference writes bins[nbins] for the maximum voxel (Voltool.C:457) */
   long *tmp = new long[nbins + 1];

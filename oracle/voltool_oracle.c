@@ -495,6 +495,36 @@ void vo_vol_com(const vo_grid *g, const float *d, float com[3]) {
   com[0] = scale * com[0]; com[1] = scale * com[1]; com[2] = scale * com[2];
 }
 
+/* Voltool.C:379-391: the origin goes through float (the map is snapped to float precision) */
+void vo_vol_moveto(vo_grid *g, const float com[3], const float pos[3]) {
+  float origin[3] = {(float)g->origin[0], (float)g->origin[1], (float)g->origin[2]};
+  for (int k = 0; k < 3; k++) {
+    float t = pos[k] - com[k];
+    origin[k] = origin[k] + t;
+  }
+  for (int k = 0; k < 3; k++) g->origin[k] = origin[k];
+}
+
+/* Voltool.C:399-438: origin = R*origin + t in float; axes = R*axis (double * float products,
+   summed in double, stored through float: vectrans, utilities.h:244-248) */
+void vo_vol_move(vo_grid *g, const float mat[16]) {
+  float origin[3] = {(float)g->origin[0], (float)g->origin[1], (float)g->origin[2]};
+  float np[3];
+  np[0] = origin[0] * mat[0] + origin[1] * mat[4] + origin[2] * mat[8];
+  np[1] = origin[0] * mat[1] + origin[1] * mat[5] + origin[2] * mat[9];
+  np[2] = origin[0] * mat[2] + origin[1] * mat[6] + origin[2] * mat[10];
+  for (int k = 0; k < 3; k++) { float s = np[k] + mat[12 + k]; g->origin[k] = s; }
+  double *axes[3] = {g->xaxis, g->yaxis, g->zaxis};
+  for (int a = 0; a < 3; a++) {
+    double v[3] = {axes[a][0], axes[a][1], axes[a][2]};
+    float r[3];
+    r[0] = (float)(v[0] * mat[0] + v[1] * mat[4] + v[2] * mat[8]);
+    r[1] = (float)(v[0] * mat[1] + v[1] * mat[5] + v[2] * mat[9]);
+    r[2] = (float)(v[0] * mat[2] + v[1] * mat[6] + v[2] * mat[10]);
+    for (int k = 0; k < 3; k++) axes[a][k] = r[k];
+  }
+}
+
 /* Voltool.C:443-461.  The reference indexes bins[nbins] for the maximum voxel (out of bounds);
    here that count is dropped instead of corrupting memory. */
 void vo_histogram(const vo_grid *g, const float *d, vo_cache *c, int nbins, long *bins, float *midpts) {

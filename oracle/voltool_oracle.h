@@ -86,6 +86,8 @@ float vo_sigma(const vo_grid *g, const float *d, vo_cache *c);
 void vo_minmax_1fv(const float *f, long n, float *mn, float *mx);
 void vo_minmaxmean_1fv(const float *f, long n, float *mn, float *mx, float *mean);
 void vo_vol_com(const vo_grid *g, const float *d, float com[3]);
+void vo_vol_moveto(vo_grid *g, const float com[3], const float pos[3]);
+void vo_vol_move(vo_grid *g, const float mat[16]);
 void vo_histogram(const vo_grid *g, const float *d, vo_cache *c, int nbins, long *bins, float *midpts);
 
 /* ---- resizing ops [PINNED] (data reallocated with malloc; old buffer freed by caller) ---- */

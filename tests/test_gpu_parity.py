@@ -348,3 +348,16 @@ def test_fit_matches_oracle(oracle):
     assert abs(r_got.best_cc - r_want.best_cc) <= 1e-5 * abs(r_want.best_cc)
     assert np.array_equal(bits(np.array(r_got.dencom)), bits(np.array(r_want.dencom)))
     assert np.array_equal(bits(p_got), bits(p_want.reshape(-1, 3)))
+
+
+def test_vol_move_moveto(oracle):
+    r = np.random.default_rng(12)
+    for g in grids():
+        d = rng_map(1, g.n)
+        com, pos = r.normal(size=3).astype(np.float32) * 10, r.normal(size=3).astype(np.float32) * 10
+        assert vt.VolMap(G(g), d).vol_moveto(com, pos).grid.astuple() == oracle.vol_moveto(g, com, pos).astuple()
+        a = 0.7
+        mat = np.array([np.cos(a), np.sin(a), 0, 0, -np.sin(a), np.cos(a), 0, 0, 0, 0, 1, 0, 3.25, -1.5, 0.125, 1], np.float32)
+        m = vt.VolMap(G(g), d).vol_move(mat)
+        assert m.grid.astuple() == oracle.vol_move(g, mat).astuple()
+        assert np.array_equal(bits(m.data), bits(d))

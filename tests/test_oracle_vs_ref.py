@@ -182,3 +182,14 @@ def test_blur_route(oracle, ref):
     v = ref.vol(g, d).op("blur", 1.5)
     assert np.array_equal(bits(oracle.blur(g, d, 1.5)), bits(v.data))
     assert v.cache.astuple()[:3] == (0, 0, 0)
+
+
+def test_vol_move_moveto_bit_exact(oracle, ref):
+    r = np.random.default_rng(12)
+    for g in grids():
+        d = rng_map(1, g.n)
+        com, pos = r.normal(size=3).astype(np.float32) * 10, r.normal(size=3).astype(np.float32) * 10
+        assert oracle.vol_moveto(g, com, pos).astuple() == ref.vol(g, d).moveto(com, pos).grid.astuple()
+        a = 0.7
+        mat = np.array([np.cos(a), np.sin(a), 0, 0, -np.sin(a), np.cos(a), 0, 0, 0, 0, 1, 0, 3.25, -1.5, 0.125, 1], np.float32)
+        assert oracle.vol_move(g, mat).astuple() == ref.vol(g, d).move(mat).grid.astuple()

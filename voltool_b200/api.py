@@ -135,6 +135,8 @@ def lib():
     L.vt_sigma.argtypes = [M, c_float_p]
     L.vt_vol_com.argtypes = [M, c_float_p]
     L.vt_histogram.argtypes = [M, C.c_int, C.POINTER(C.c_long), c_float_p]
+    L.vt_vol_moveto.argtypes = [M, c_float_p, c_float_p]
+    L.vt_vol_move.argtypes = [M, c_float_p]
     L.vt_pad.argtypes = [M] + [C.c_int] * 6
     L.vt_crop.argtypes = [M] + [C.c_double] * 6
     L.vt_downsample.argtypes = [M]
@@ -349,6 +351,15 @@ class VolMap:
         com = np.zeros(3, np.float32)
         _check(lib().vt_vol_com(self.h, com.ctypes.data_as(c_float_p)), "vt_vol_com")
         return com
+
+    def vol_moveto(self, com, pos):
+        a, ka = _fp3(com)
+        b, kb = _fp3(pos)
+        _check(lib().vt_vol_moveto(self.h, a, b), "vt_vol_moveto"); return self
+
+    def vol_move(self, mat):
+        m = f32(mat).reshape(-1)
+        _check(lib().vt_vol_move(self.h, m.ctypes.data_as(c_float_p)), "vt_vol_move"); return self
 
     def histogram(self, nbins=10):
         bins = (C.c_long * nbins)()

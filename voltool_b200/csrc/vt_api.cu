@@ -200,6 +200,16 @@ int vt_vol_com(const vt_map *m, float com[3]) {
   return 0;
 }
 
+int vt_vol_moveto(vt_map *m, const float com[3], const float pos[3]) {
+  vol_moveto(m->grid, com, pos);
+  return 0;
+}
+
+int vt_vol_move(vt_map *m, const float mat[16]) {
+  vol_move(m->grid, mat);
+  return 0;
+}
+
 int vt_histogram(vt_map *m, int nbins, long *bins, float *midpts) {
   VT_REQUIRE_CTX();
   if (nbins < 1 || nbins > 8192) { set_error("vt_histogram: nbins out of range"); return 1; }

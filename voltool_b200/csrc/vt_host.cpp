@@ -119,6 +119,32 @@ void supersample_geom(vt_grid &g) {
   g.xsize = g.xsize * 2 - 1; g.ysize = g.ysize * 2 - 1; g.zsize = g.zsize * 2 - 1;  // axes unchanged
 }
 
+// vol_moveto: translate the map so that `com` lands on `pos`; the origin is carried in float
+void vol_moveto(vt_grid &g, const float com[3], const float pos[3]) {
+  for (int k = 0; k < 3; ++k) {
+    const float o = (float)g.origin[k];
+    const float shift = pos[k] - com[k];
+    const float moved = o + shift;
+    g.origin[k] = moved;
+  }
+}
+
+// vol_move: rigid transform of the map frame by a column-major 4x4; origin in float, axes via
+// vectrans (double * float summed in double, stored through float)
+void vol_move(vt_grid &g, const float m[16]) {
+  const float o[3] = {(float)g.origin[0], (float)g.origin[1], (float)g.origin[2]};
+  for (int k = 0; k < 3; ++k) {
+    const float rot = o[0] * m[k] + o[1] * m[4 + k] + o[2] * m[8 + k];
+    const float moved = rot + m[12 + k];
+    g.origin[k] = moved;
+  }
+  double *axes[3] = {g.xaxis, g.yaxis, g.zaxis};
+  for (int a = 0; a < 3; ++a) {
+    const double v[3] = {axes[a][0], axes[a][1], axes[a][2]};
+    for (int k = 0; k < 3; ++k) axes[a][k] = (float)(v[0] * m[k] + v[1] * m[4 + k] + v[2] * m[8 + k]);
+  }
+}
+
 double cc_from_sums(const double s[5], long n) {
   const int size = (int)n;
   const double mA = s[0] / size, mB = s[1] / size;

@@ -55,6 +55,8 @@ void crop_pads(const vt_grid &g, double minx, double miny, double minz, double m
 void downsample_geom(vt_grid &g);                                         // VolumetricData.C:744-757
 void supersample_geom(vt_grid &g);                                        // VolumetricData.C:778-781, 915-917
 
+void vol_moveto(vt_grid &g, const float com[3], const float pos[3]);      // Voltool.C:379-391
+void vol_move(vt_grid &g, const float mat[16]);                           // Voltool.C:399-438
 double cc_from_sums(const double s[5], long n);                           // MDFF.C:143-149
 int blur_taps(double sigma, float *w, int maxw);                          // GaussianBlur restatement
 
