@@ -19,7 +19,8 @@ struct SimParams {
 };
 
 // splat tile (voxels) and staging sizes
-constexpr int kTX = 16, kTY = 16, kTZ = 8;
+constexpr int kSplatWarps = 4;                 // warps per splat CTA: regions are 8x8x4, 2 in x, kSplatWarps/4 in y, 2 in z
+constexpr int kTX = 16, kTY = 2 * kSplatWarps, kTZ = 8;
 constexpr int kChunk = 64;     // atoms staged per compute round
 constexpr int kRec = 44;       // floats per staged atom record
 constexpr int kMaxIds = 2048;  // gathered atom ids per flush

@@ -420,7 +420,7 @@ __device__ __forceinline__ int find_pose(const PoseGeom *__restrict__ geo, int n
 
 constexpr int kWRec = 20;     // floats per warp-staged atom: Ex[8] | dy^2[8] | dz^2[4]
 constexpr int kGChunk = 1024; // groups expanded from the bitmap at a time (32 words, one warp)
-constexpr int kWGroups = 32;  // groups a warp gathers per batch
+constexpr int kWGroups = 48;  // groups a warp gathers per batch
 constexpr int kWList = kWGroups * 32;  // per-warp gathered atoms per batch
 
 // Which groups can touch which tile: thread per (pose, group) marks the tiles its bounding sphere
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(256) pose_bin_kernel(const PoseGeom *__restric
   }
 }
 
-__global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
+__global__ void __launch_bounds__(32 * kSplatWarps, (kSplatWarps == 4 ? 6 : 3)) splat_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
                                                        int npose, int natoms, int ngroups,
                                                        const float4 *__restrict__ tpos_all,
                                                        const unsigned int *__restrict__ bitmap, int tiles_cap, int nwords,
@@ -467,19 +467,21 @@ __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restric
                                                        float *__restrict__ grid_all, long cap_grid) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   float(*s_rec)[32 * kWRec] = reinterpret_cast<float(*)[32 * kWRec]>(s_dyn);          // warp-private staged records
-  unsigned short(*s_wid)[kWList] = reinterpret_cast<unsigned short(*)[kWList]>(s_dyn + sizeof(float) * 8 * 32 * kWRec);
-  unsigned char(*s_wm)[kWList] = reinterpret_cast<unsigned char(*)[kWList]>(s_dyn + sizeof(float) * 8 * 32 * kWRec +
-                                                                            sizeof(unsigned short) * 8 * kWList);
+  constexpr int W = kSplatWarps;
+  unsigned short(*s_wid)[kWList] = reinterpret_cast<unsigned short(*)[kWList]>(s_dyn + sizeof(float) * W * 32 * kWRec);
+  unsigned char(*s_wm)[kWList] = reinterpret_cast<unsigned char(*)[kWList]>(s_dyn + sizeof(float) * W * 32 * kWRec +
+                                                                            sizeof(unsigned short) * W * kWList);
   // s_wid: atoms gathered by warp w whose box meets this tile, as (index in s_glist) << 5 | lane;
   // s_wm: which of the 8 warp regions they meet
-  __shared__ float s_ar[8][32], s_rl2[8][32];           // arinv, (gausslim*sigma)^2 per staged atom
-  __shared__ int s_pend[8][64];                         // warp-private pending ids
-  __shared__ int s_wn[8];
+  __shared__ float s_ar[W][32], s_rl2[W][32];           // arinv, (gausslim*sigma)^2 per staged atom
+  __shared__ int s_pend[W][64];                         // warp-private pending ids
+  __shared__ int s_wn[W];
   __shared__ unsigned short s_glist[kGChunk];           // groups (offsets inside the chunk) that can reach the tile
   __shared__ int s_scan[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned int lt = (1u << lane) - 1u;
-  const int wx = warp & 1, wy = (warp >> 1) & 1, wz = warp >> 2;
+  // region of warp w: x half (w & 1), z half ((w >> 1) & 1), y block (w >> 2)
+  const int wx = warp & 1, wz = (warp >> 1) & 1, wy = warp >> 2;
   const int total = totals[0];
 
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restric
     // its own region
     auto drain = [&](int gbase) {
       int have = 0;
-      for (int l = 0; l < 8; ++l) {
+      for (int l = 0; l < W; ++l) {
         const int count = s_wn[l];
         for (int b0 = 0; b0 < count; b0 += 32) {
           const int i = b0 + lane;
@@ -614,11 +616,11 @@ __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restric
       }
       __syncthreads();
       const int nhit = s_scan[0];
-      for (int b0 = 0; b0 < nhit; b0 += 8 * kWGroups) {
+      for (int b0 = 0; b0 < nhit; b0 += W * kWGroups) {
         // each warp tests the atoms of up to kWGroups groups with the reference's truncated integer box
         int cnt = 0;
         for (int j = 0; j < kWGroups; ++j) {
-          const int gi = b0 + warp + 8 * j;
+          const int gi = b0 + warp + W * j;
           if (gi >= nhit) break;
           const int id = (w0 * 32 + (int)s_glist[gi]) * 32 + lane;
           bool take = false;
@@ -636,13 +638,14 @@ __global__ void __launch_bounds__(256, 3) splat_kernel(const PoseGeom *__restric
             take = xmin <= x0 + kTX - 1 && xmax >= x0 && ymin <= y0 + kTY - 1 && ymax >= y0 && zmin <= z0 + kTZ - 1 &&
                    zmax >= z0 && xmin <= xmax && ymin <= ymax && zmin <= zmax;
             if (take) {
-              // bit w: box meets warp region w = (wx, wy, wz) = (w&1, (w>>1)&1, w>>2)
+              // bit w: box meets the region of warp w (x half w&1, z half (w>>1)&1, y block w>>2)
               const int mx = (xmin <= x0 + 7 ? 1 : 0) | (xmax >= x0 + 8 ? 2 : 0);
-              const int my = (ymin <= y0 + 7 ? 1 : 0) | (ymax >= y0 + 8 ? 2 : 0);
               const int mz = (zmin <= z0 + 3 ? 1 : 0) | (zmax >= z0 + 4 ? 2 : 0);
 #pragma unroll
-              for (int w = 0; w < 8; ++w)
-                if (((mx >> (w & 1)) & 1) && ((my >> ((w >> 1) & 1)) & 1) && ((mz >> (w >> 2)) & 1)) mask |= 1 << w;
+              for (int w = 0; w < W; ++w) {
+                const int yb = y0 + 8 * (w >> 2);
+                if (((mx >> (w & 1)) & 1) && ((mz >> ((w >> 1) & 1)) & 1) && ymin <= yb + 7 && ymax >= yb) mask |= 1 << w;
+              }
             }
           }
           const unsigned int b2 = __ballot_sync(0xffffffffu, take);
@@ -683,15 +686,15 @@ int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
                                                           pb.d_bitmap, pb.tiles_cap, nwords);
   prof_end(PK_SETUP);
   VT_LAUNCHED();
-  const int grid = c.sm_count * 3 * 4;  // persistent: 3 resident CTAs per SM, 4 rounds for uneven tiles
+  const int grid = c.sm_count * (kSplatWarps == 4 ? 6 : 3) * 4;  // persistent: resident CTAs per SM x 4 rounds
   prof_begin(PK_SPLAT);
-  const size_t smem = sizeof(float) * 8 * 32 * kWRec + (sizeof(unsigned short) + 1) * 8 * kWList;
+  const size_t smem = sizeof(float) * kSplatWarps * 32 * kWRec + (sizeof(unsigned short) + 1) * kSplatWarps * kWList;
   static bool attr = false;
   if (!attr) {
     VT_CUDA(cudaFuncSetAttribute(splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  splat_kernel<<<grid, 256, smem, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, as.ngroups, pb.d_tpos, pb.d_bitmap,
+  splat_kernel<<<grid, 32 * kSplatWarps, smem, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, as.ngroups, pb.d_tpos, pb.d_bitmap,
                                            pb.tiles_cap, nwords, as.d_const, as.prm.gs, as.prm.invgs, pb.d_grid, pb.cap_grid);
   prof_end(PK_SPLAT);
   VT_LAUNCHED();
