@@ -290,9 +290,14 @@ def extra_ops(vt, peaks, args):
     gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
     res["correlate"] = {"map": [n, n, n], "ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8,
                         "cc": vt.cc_threaded(A, B)}
+    ms = timeit("binary", lambda: vt.add(A, B))
+    gbs = 12.0 * g.n / (ms * 1e-3) / 1e9
+    res["add"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 12}
     ms = timeit("unary", lambda: A.scalar_add(0.0))
     gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
     res["sadd"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8}
+    ms = timeit("unary", lambda: A.clone().binmask(0.5))
+    res["binmask"] = {"ms": ms, "GB/s": 8.0 * g.n / (ms * 1e-3) / 1e9, "bytes_per_voxel": 8}
     ms = timeit("stats", lambda: (A.scalar_add(0.0), A.sigma()))   # sadd invalidates mean+sigma -> 2 passes
     res["sigma"] = {"ms": ms, "GB/s": 8.0 * g.n / (ms * 1e-3) / 1e9, "bytes_per_voxel": 8, "note": "mean pass + sigma pass"}
     C = A.clone()

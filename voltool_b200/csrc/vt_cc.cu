@@ -217,9 +217,11 @@ int k_cc(const vt_map *A, const vt_map *B, double thr, double sums[5], long *n) 
 
 // ------------------------------------------------------------------------------------------ two-map ops
 template <int OP, bool INTERP, bool UNION>
-__global__ void __launch_bounds__(kThreads) binary_kernel(DevMap A, DevMap B, DevCoord C, float *__restrict__ out) {
-  const long rows = (long)C.ny * C.nz;
-  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+__global__ void __launch_bounds__(kThreads) binary_kernel(DevMap A, DevMap B, DevCoord C, float *__restrict__ out,
+                                                          int zbeg, int zend) {
+  const long rows = (long)C.ny * (zend - zbeg);
+  for (long row0 = blockIdx.x; row0 < rows; row0 += gridDim.x) {
+    const long row = row0 + (long)zbeg * C.ny;
     const int gy = (int)(row % C.ny), gz = (int)(row / C.ny);
     for (int gx = threadIdx.x; gx < C.nx; gx += blockDim.x) {
       float x, y, z;
@@ -248,15 +250,37 @@ __global__ void __launch_bounds__(kThreads) binary_kernel(DevMap A, DevMap B, De
 
 template <int OP>
 static void launch_binary(int interp, int use_union, int grid, const DevMap &A, const DevMap &B, const DevCoord &C,
-                          float *out) {
+                          float *out, int zbeg, int zend) {
   cudaStream_t s = ctx().stream;
   if (interp) {
-    if (use_union) binary_kernel<OP, true, true><<<grid, kThreads, 0, s>>>(A, B, C, out);
-    else binary_kernel<OP, true, false><<<grid, kThreads, 0, s>>>(A, B, C, out);
+    if (use_union) binary_kernel<OP, true, true><<<grid, kThreads, 0, s>>>(A, B, C, out, zbeg, zend);
+    else binary_kernel<OP, true, false><<<grid, kThreads, 0, s>>>(A, B, C, out, zbeg, zend);
   } else {
-    if (use_union) binary_kernel<OP, false, true><<<grid, kThreads, 0, s>>>(A, B, C, out);
-    else binary_kernel<OP, false, false><<<grid, kThreads, 0, s>>>(A, B, C, out);
+    if (use_union) binary_kernel<OP, false, true><<<grid, kThreads, 0, s>>>(A, B, C, out, zbeg, zend);
+    else binary_kernel<OP, false, false><<<grid, kThreads, 0, s>>>(A, B, C, out, zbeg, zend);
   }
+}
+
+int k_binary_staged(int mode, const DevMap &A, const DevMap &B, const DevCoord &C, int nx, int ny, int nz,
+                    const std::vector<AxisEntry> &host_tab, const int off[6], const AxisEntry *d_tab, float *outp,
+                    int *zlo, int *zhi);
+
+static int binary_generic(int op, int interp, int use_union, const DevMap &dA, const DevMap &dB, const DevCoord &dC,
+                          float *out, int zbeg, int zend) {
+  const long rows = (long)dC.ny * (zend - zbeg);
+  if (rows <= 0 || dC.nx <= 0) return 0;
+  int grid = (int)(rows < (long)ctx().sm_count * 8 ? rows : (long)ctx().sm_count * 8);
+  prof_begin(PK_BINARY);
+  switch (op) {
+    case VT_ADD: launch_binary<VT_ADD>(interp, use_union, grid, dA, dB, dC, out, zbeg, zend); break;
+    case VT_SUBTRACT: launch_binary<VT_SUBTRACT>(interp, use_union, grid, dA, dB, dC, out, zbeg, zend); break;
+    case VT_MULTIPLY: launch_binary<VT_MULTIPLY>(interp, use_union, grid, dA, dB, dC, out, zbeg, zend); break;
+    case VT_AVERAGE: launch_binary<VT_AVERAGE>(interp, use_union, grid, dA, dB, dC, out, zbeg, zend); break;
+    default: set_error("vt_binary: unknown op %d", op); return 1;
+  }
+  prof_end(PK_BINARY);
+  VT_LAUNCHED();
+  return 0;
 }
 
 int k_binary(int op, int interp, int use_union, const vt_map *A, const vt_map *B, const vt_grid &og, float *out) {
@@ -266,20 +290,30 @@ int k_binary(int op, int interp, int use_union, const vt_map *A, const vt_map *B
   to_dev(A, !interp, dA);
   to_dev(B, !interp, dB);
   to_dev(og, dC);
-  const long rows = (long)og.ysize * og.zsize;
-  if (rows <= 0 || og.xsize <= 0) return 0;
-  int grid = (int)(rows < (long)ctx().sm_count * 8 ? rows : (long)ctx().sm_count * 8);
-  prof_begin(PK_BINARY);
-  switch (op) {
-    case VT_ADD: launch_binary<VT_ADD>(interp, use_union, grid, dA, dB, dC, out); break;
-    case VT_SUBTRACT: launch_binary<VT_SUBTRACT>(interp, use_union, grid, dA, dB, dC, out); break;
-    case VT_MULTIPLY: launch_binary<VT_MULTIPLY>(interp, use_union, grid, dA, dB, dC, out); break;
-    case VT_AVERAGE: launch_binary<VT_AVERAGE>(interp, use_union, grid, dA, dB, dC, out); break;
-    default: set_error("vt_binary: unknown op %d", op); return 1;
+  if ((long)og.ysize * og.zsize <= 0 || og.xsize <= 0) return 0;
+  const long vox = (long)og.xsize * og.ysize * og.zsize;
+  // large interpolated ops on orthogonal cells stream through the shared-memory ring; voxels whose
+  // result involves a NaN are redone there with the literal arithmetic, so the bits are the same
+  const char *force = getenv("VOLTOOL_CC_STAGED");
+  const bool want_staged = interp && (force ? atoi(force) != 0 : vox >= (8L << 20)) && axis_aligned_out(dC) &&
+                           diagonal_inverse(dA.inv) && diagonal_inverse(dB.inv) && finite_geom(dC) &&
+                           !getenv("VOLTOOL_FORCE_GENERIC");
+  if (want_staged) {
+    SepTables T;
+    int rc = upload_tables(dC, dA, dB, T);
+    if (rc) return rc;
+    const int mode = op == VT_ADD ? 1 : op == VT_SUBTRACT ? 2 : op == VT_MULTIPLY ? (use_union ? 4 : 3) : 5;
+    int zlo = 0, zhi = 0;
+    const int st = k_binary_staged(mode, dA, dB, dC, og.xsize, og.ysize, og.zsize, T.host, T.off, T.d, out, &zlo, &zhi);
+    dev_free(T.d);
+    if (st > 1) return st;
+    if (st == 0) {
+      rc = binary_generic(op, interp, use_union, dA, dB, dC, out, 0, zlo);
+      if (!rc) rc = binary_generic(op, interp, use_union, dA, dB, dC, out, zhi, og.zsize);
+      return rc;
+    }
   }
-  prof_end(PK_BINARY);
-  VT_LAUNCHED();
-  return 0;
+  return binary_generic(op, interp, use_union, dA, dB, dC, out, 0, og.zsize);
 }
 
 }  // namespace vt

@@ -213,13 +213,22 @@ __device__ __forceinline__ void producer_run(const float *__restrict__ src, int 
   }
 }
 
-template <int Y>
+// MODE 0: cross correlation sums.  MODE 1..5: two-map op written to outp (Voltool.C:249-377):
+// 1 add, 2 subtract, 3 multiply (intersection rule), 4 multiply (union NaN rule), 5 average.
+struct BinaryArgs {
+  float *outp;
+  DevMap gA, gB;   // for the exact re-evaluation of voxels whose result is a NaN (payload rules)
+  DevCoord gC;
+};
+
+template <int Y, int MODE>
 __global__ void __launch_bounds__(kThreadsStaged, (Y > 4 ? 1 : 2))
     cc_staged_kernel(const float *__restrict__ A, int anx, int any, const float *__restrict__ B, int bnx, int bny,
                      const AxisEntry *__restrict__ tAx, const AxisEntry *__restrict__ tAy,
                      const AxisEntry *__restrict__ tAz, const AxisEntry *__restrict__ tBx,
                      const AxisEntry *__restrict__ tBy, const AxisEntry *__restrict__ tBz, int nx, int ny, int nz,
-                     int zchunk, int zlo, int zhi, float thr_f, double *partials, unsigned int *ticket, double *out) {
+                     int zchunk, int zlo, int zhi, float thr_f, double *partials, unsigned int *ticket, double *out,
+                     BinaryArgs ba) {
   constexpr int TY = Shape<Y>::TY, YS = Shape<Y>::YS;
   constexpr int plane_floats = YS * XS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -266,35 +275,68 @@ __global__ void __launch_bounds__(kThreadsStaged, (Y > 4 ? 1 : 2))
       Consumer<Y> ca, cb;
       consumer_init<Y>(ca, ax, tAy, gy0, ny, bA);
       consumer_init<Y>(cb, bx, tBy, gy0, ny, bB);
-      bool ok[Y];
+      bool ok[Y], inA[Y], inB[Y];
 #pragma unroll
       for (int r = 0; r < Y; ++r) {
         const int gy = gy0 + r, gyc = min(gy, ny - 1);
-        ok[r] = gx < nx && gy < ny && ax.inside && bx.inside && tAy[gyc].inside && tBy[gyc].inside;
+        inA[r] = ax.inside && tAy[gyc].inside;
+        inB[r] = bx.inside && tBy[gyc].inside;
+        ok[r] = gx < nx && gy < ny;
       }
       for (int gz = za; gz < zb; ++gz) {
         const AxisEntry az = tAz[gz], bz = tBz[gz];
         float va[Y], vb[Y];
         consumer_sample<Y>(ca, az, ringA, fullA, emptyA, cntA, plane_floats, va);
         consumer_sample<Y>(cb, bz, ringB, fullB, emptyB, cntB, plane_floats, vb);
-        float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;
-        int cnt = 0;
+        if (MODE == 0) {
+          float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;
+          int cnt = 0;
 #pragma unroll
-        for (int r = 0; r < Y; ++r) {
-          const bool take = ok[r] && (va[r] == va[r]) && (va[r] >= thr_f) && (vb[r] == vb[r]);  // MDFF.C:73-77
-          const float a = take ? va[r] : 0.f, b = take ? vb[r] : 0.f;
-          fA += a; fB += b;
-          fAA += a * a; fBB += b * b; fAB += a * b;
-          cnt += take ? 1 : 0;
+          for (int r = 0; r < Y; ++r) {
+            const bool take = ok[r] && inA[r] && inB[r] && (va[r] >= thr_f) && (vb[r] == vb[r]);  // MDFF.C:73-77
+            const float a = take ? va[r] : 0.f, b = take ? vb[r] : 0.f;
+            fA += a; fB += b;
+            fAA += a * a; fBB += b * b; fAB += a * b;
+            cnt += take ? 1 : 0;
+          }
+          acc[0] += (double)fA; acc[1] += (double)fB; acc[2] += (double)fAA; acc[3] += (double)fBB;
+          acc[4] += (double)fAB;
+          nvox += cnt;
+        } else {
+          constexpr bool SAFE = (MODE != 3 && MODE != 4);  // add/sub/avg read 0 outside, multiply reads NaN
+#pragma unroll
+          for (int r = 0; r < Y; ++r) {
+            if (!ok[r]) continue;
+            const int gy = gy0 + r;
+            float a = inA[r] ? va[r] : (SAFE ? 0.0f : quiet_nan());
+            float b = inB[r] ? vb[r] : (SAFE ? 0.0f : quiet_nan());
+            if (a != a || b != b) {
+              // a NaN is involved: redo this voxel with the literal per-voxel arithmetic so that the
+              // x86 payload rules of the reference are reproduced
+              float x, y, z;
+              voxel_coord(ba.gC, gx, gy, gz, x, y, z);
+              a = sample_interp<SAFE>(ba.gA, x, y, z);
+              b = sample_interp<SAFE>(ba.gB, x, y, z);
+            }
+            float v;
+            if (MODE == 1) v = nan_like_x86(a + b, a, b);
+            else if (MODE == 2) v = nan_like_x86(a - b, a, b);
+            else if (MODE == 3) v = nan_like_x86(a * b, a, b);
+            else if (MODE == 4) {
+              const bool na = is_nan_bits(a), nb = is_nan_bits(b);
+              v = (!na && !nb) ? nan_like_x86(a * b, a, b) : (!na ? a : (!nb ? b : 0.0f));
+            } else v = nan_like_x86((float)((double)(a + b) * 0.5), a, b);
+            ba.outp[((size_t)gz * ny + gy) * nx + gx] = v;
+          }
         }
-        acc[0] += (double)fA; acc[1] += (double)fB; acc[2] += (double)fAA; acc[3] += (double)fBB; acc[4] += (double)fAB;
-        nvox += cnt;
       }
     }
   }
-  acc[5] = (double)nvox;
-  block_sum<6>(acc, sm);
-  grid_finish<6>(acc, partials, ticket, out, sm);
+  if (MODE == 0) {
+    acc[5] = (double)nvox;
+    block_sum<6>(acc, sm);
+    grid_finish<6>(acc, partials, ticket, out, sm);
+  }
 }
 
 }  // namespace staged
@@ -343,26 +385,27 @@ static bool staged_ok(const std::vector<AxisEntry> &tab, const int off[6], int n
   return true;
 }
 
-template <int Y>
+template <int Y, int MODE>
 static int launch_staged(const DevMap &A, const DevMap &B, int nx, int ny, int nz, const std::vector<AxisEntry> &host_tab,
                          const int off[6], const AxisEntry *d_tab, float thr_f, double *partials, unsigned int *ticket,
-                         double *dout) {
+                         double *dout, const staged::BinaryArgs &ba, int *zlo_out, int *zhi_out) {
   using namespace staged;
   int zlo, zhi;
   if (!staged_ok<Y>(host_tab, off, nx, ny, nz, A.nx, B.nx, zlo, zhi)) return 1;
+  if (zlo_out) { *zlo_out = zlo; *zhi_out = zhi; }
   Ctx &c = ctx();
   constexpr int TY = Shape<Y>::TY, YS = Shape<Y>::YS;
   const size_t smem = sizeof(float) * 2 * (size_t)S * YS * XS + sizeof(unsigned long long) * 4 * S;
-  VT_CUDA(cudaFuncSetAttribute(cc_staged_kernel<Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VT_CUDA(cudaFuncSetAttribute(cc_staged_kernel<Y, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int zchunk = 64;
   const long work = (long)((nx + TX - 1) / TX) * ((ny + TY - 1) / TY) * ((zhi - zlo + zchunk - 1) / zchunk);
   int grid = (int)std::min<long>(work, (long)c.sm_count * (Y > 4 ? 1 : 2));
-  prof_begin(PK_CC);
-  cc_staged_kernel<Y><<<grid, kThreadsStaged, smem, c.stream>>>(A.d, A.nx, A.ny, B.d, B.nx, B.ny, d_tab + off[0],
-                                                                 d_tab + off[1], d_tab + off[2], d_tab + off[3],
-                                                                 d_tab + off[4], d_tab + off[5], nx, ny, nz, zchunk, zlo,
-                                                                 zhi, thr_f, partials, ticket, dout);
-  prof_end(PK_CC);
+  prof_begin(MODE == 0 ? PK_CC : PK_BINARY);
+  cc_staged_kernel<Y, MODE><<<grid, kThreadsStaged, smem, c.stream>>>(A.d, A.nx, A.ny, B.d, B.nx, B.ny, d_tab + off[0],
+                                                                       d_tab + off[1], d_tab + off[2], d_tab + off[3],
+                                                                       d_tab + off[4], d_tab + off[5], nx, ny, nz, zchunk,
+                                                                       zlo, zhi, thr_f, partials, ticket, dout, ba);
+  prof_end(MODE == 0 ? PK_CC : PK_BINARY);
   VT_LAUNCHED();
   return 0;
 }
@@ -371,9 +414,25 @@ static int launch_staged(const DevMap &A, const DevMap &B, int nx, int ny, int n
 int k_cc_staged(const DevMap &A, const DevMap &B, int nx, int ny, int nz, const std::vector<AxisEntry> &host_tab,
                 const int off[6], const AxisEntry *d_tab, float thr_f, double *partials, unsigned int *ticket,
                 double *dout) {
-  const char *e = getenv("VOLTOOL_CC_Y");
-  if (e && atoi(e) == 8) return launch_staged<8>(A, B, nx, ny, nz, host_tab, off, d_tab, thr_f, partials, ticket, dout);
-  return launch_staged<4>(A, B, nx, ny, nz, host_tab, off, d_tab, thr_f, partials, ticket, dout);
+  staged::BinaryArgs ba{};
+  return launch_staged<4, 0>(A, B, nx, ny, nz, host_tab, off, d_tab, thr_f, partials, ticket, dout, ba, nullptr, nullptr);
+}
+
+// two-map op through the ring: writes the planes [zlo, zhi) in which both maps are sampled; the
+// caller fills the rest with the generic kernel.  mode as in cc_staged_kernel.
+int k_binary_staged(int mode, const DevMap &A, const DevMap &B, const DevCoord &C, int nx, int ny, int nz,
+                    const std::vector<AxisEntry> &host_tab, const int off[6], const AxisEntry *d_tab, float *outp,
+                    int *zlo, int *zhi) {
+  staged::BinaryArgs ba;
+  ba.outp = outp; ba.gA = A; ba.gB = B; ba.gC = C;
+  switch (mode) {
+    case 1: return launch_staged<4, 1>(A, B, nx, ny, nz, host_tab, off, d_tab, 0.f, nullptr, nullptr, nullptr, ba, zlo, zhi);
+    case 2: return launch_staged<4, 2>(A, B, nx, ny, nz, host_tab, off, d_tab, 0.f, nullptr, nullptr, nullptr, ba, zlo, zhi);
+    case 3: return launch_staged<4, 3>(A, B, nx, ny, nz, host_tab, off, d_tab, 0.f, nullptr, nullptr, nullptr, ba, zlo, zhi);
+    case 4: return launch_staged<4, 4>(A, B, nx, ny, nz, host_tab, off, d_tab, 0.f, nullptr, nullptr, nullptr, ba, zlo, zhi);
+    case 5: return launch_staged<4, 5>(A, B, nx, ny, nz, host_tab, off, d_tab, 0.f, nullptr, nullptr, nullptr, ba, zlo, zhi);
+  }
+  return 1;
 }
 
 }  // namespace vt
