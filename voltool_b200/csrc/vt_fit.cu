@@ -74,7 +74,13 @@ int sim_to_map(const float *pos, const float *radii, long natoms, int quality, f
   if (!rc) rc = dev_alloc((void **)&pb.d_bitmap, sizeof(unsigned int) * (size_t)pb.tiles_cap * ((as.ngroups + 31) / 32));
   const float com0[3] = {0.f, 0.f, 0.f};
   if (!rc) rc = batch_prepare(as, pb, 1, nullptr, com0, 1, nullptr);
+  if (!rc) rc = batch_calibrate_lists(as, pb);
   if (!rc) rc = batch_splat(as, pb, 1);
+  if (!rc && pb.use_lists) {
+    int ovf = 0;
+    rc = batch_lists_overflowed(pb, &ovf);
+    if (!rc && ovf) { pb.use_lists = false; rc = batch_splat(as, pb, 1); }
+  }
   PoseGeom G;
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(&G, pb.d_geom, sizeof(G), cudaMemcpyDeviceToHost, c.stream);
@@ -215,6 +221,11 @@ int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_ma
   if (f->B > 1024) f->B = 1024;
   rc = batch_create(f->as, &target->grid, f->B, f->pb);
   if (!rc) {
+    const float com0[3] = {0.f, 0.f, 0.f};
+    rc = batch_prepare(f->as, f->pb, 1, nullptr, com0, 1, &target->grid);
+    if (!rc) rc = batch_calibrate_lists(f->as, f->pb);
+  }
+  if (!rc) {
     cudaError_t e = cudaMallocHost((void **)&f->h_prep, sizeof(PrepPose) * f->B);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
   }
@@ -245,6 +256,7 @@ int vt_fit_eval_poses(vt_fit_ctx *f, const float com[3], const vt_pose *poses, l
   int rc = ensure_cc_buffer(f, nposes);
   if (rc) return rc;
   Ctx &c = ctx();
+  if (f->pb.use_lists) VT_CUDA(cudaMemsetAsync(f->pb.d_totals + 2, 0, sizeof(int), c.stream));
   for (long p0 = 0; p0 < nposes; p0 += f->B) {
     const int n = (int)std::min<long>(f->B, nposes - p0);
     // the pinned staging buffer is reused: wait for the previous batch's upload to be consumed
@@ -262,6 +274,15 @@ int vt_fit_eval_poses(vt_fit_ctx *f, const float com[3], const vt_pose *poses, l
   }
   VT_CUDA(cudaMemcpyAsync(cc_out, f->d_cc, sizeof(float) * (size_t)nposes, cudaMemcpyDeviceToHost, c.stream));
   VT_CUDA(cudaStreamSynchronize(c.stream));
+  if (f->pb.use_lists) {
+    int ovf = 0;
+    rc = batch_lists_overflowed(f->pb, &ovf);
+    if (rc) return rc;
+    if (ovf) {  // a tile list was too small: nothing is truncated silently, redo with the cooperative kernel
+      f->pb.use_lists = false;
+      return vt_fit_eval_poses(f, com, poses, nposes, cc_out);
+    }
+  }
   return 0;
 }
 

@@ -19,7 +19,7 @@ struct SimParams {
 };
 
 // splat tile (voxels) and staging sizes
-constexpr int kSplatWarps = 4;                 // warps per splat CTA: regions are 8x8x4, 2 in x, kSplatWarps/4 in y, 2 in z
+constexpr int kSplatWarps = 8;                 // warps per splat CTA: regions are 8x8x4, 2 in x, kSplatWarps/4 in y, 2 in z
 constexpr int kTX = 16, kTY = 2 * kSplatWarps, kTZ = 8;
 constexpr int kChunk = 64;     // atoms staged per compute round
 constexpr int kRec = 44;       // floats per staged atom record
@@ -71,6 +71,12 @@ struct PoseBatch {
   int *d_totals = nullptr;  // [0] tiles, [1] cc items
   unsigned int *d_bitmap = nullptr;  // [B][tiles_cap][ceil(ngroups/32)]: groups that can reach a tile
   int tiles_cap = 0;
+  // barrier-free splat (vt_splat2.cu): packed integer boxes, per-tile atom lists
+  uint3 *d_boxes = nullptr;          // [B][natoms]
+  unsigned int *d_tlist = nullptr;   // [B][tiles_cap][cap_t]: id | region mask << 24
+  int *d_tcount = nullptr;           // [B][tiles_cap]
+  int cap_t = 0;
+  bool use_lists = false;
   float *d_grid = nullptr;
   geom::AxisEntry *d_tab = nullptr;  // [B][6][cap_o]
   double *d_part = nullptr;          // [B][cap_items][6]
@@ -89,6 +95,13 @@ int batch_prepare(const AtomSet &as, PoseBatch &pb, int npose, const PrepPose *d
                   int identity, const vt_grid *target);
 // stage 2: splat every pose's density grid
 int batch_splat(const AtomSet &as, PoseBatch &pb, int npose);
+// size and switch on the list-based splat from the pose(s) currently prepared in pb (needs
+// batch_prepare first); leaves the cooperative kernel in place when it does not apply
+int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb);
+int batch_splat_lists(const AtomSet &as, PoseBatch &pb, int npose);
+int batch_bin(const AtomSet &as, PoseBatch &pb, int npose);
+// 1 if a tile list overflowed since the last reset (synchronises)
+int batch_lists_overflowed(PoseBatch &pb, int *flag);
 // stage 3: cc of every pose's grid against the target; d_cc[npose] floats
 int batch_cc(PoseBatch &pb, int npose, const vt_map *target, double threshold, float *d_cc, double *d_sums);
 

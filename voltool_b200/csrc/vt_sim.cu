@@ -22,6 +22,7 @@
 //   * every voxel is written exactly once (no memset, no read-modify-write).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -213,6 +214,7 @@ int batch_create(const AtomSet &as, const vt_grid *target, int B, PoseBatch &pb)
 
 void batch_destroy(PoseBatch &pb) {
   dev_free(pb.d_tpos); dev_free(pb.d_tgroup); dev_free(pb.d_bbox); dev_free(pb.d_geom); dev_free(pb.d_totals); dev_free(pb.d_bitmap);
+  dev_free(pb.d_boxes); dev_free(pb.d_tlist); dev_free(pb.d_tcount);
   dev_free(pb.d_grid); dev_free(pb.d_prep); dev_free(pb.d_tab); dev_free(pb.d_part);
   pb = PoseBatch();
 }
@@ -353,6 +355,7 @@ __global__ void __launch_bounds__(256) pose_setup_kernel(const unsigned int *__r
     }
     totals[0] = t;
     totals[1] = c;
+    totals[3] = 0;
   }
 }
 
@@ -674,7 +677,7 @@ __global__ void __launch_bounds__(32 * kSplatWarps, (kSplatWarps == 4 ? 6 : 3)) 
   }
 }
 
-int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
+int batch_bin(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
   const int nwords = (as.ngroups + 31) / 32;
@@ -686,6 +689,16 @@ int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
                                                           pb.d_bitmap, pb.tiles_cap, nwords);
   prof_end(PK_SETUP);
   VT_LAUNCHED();
+  return 0;
+}
+
+int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  int rc = batch_bin(as, pb, npose);
+  if (rc) return rc;
+  if (pb.use_lists && !getenv("VOLTOOL_SPLAT_COOP")) return batch_splat_lists(as, pb, npose);
+  const int nwords = (as.ngroups + 31) / 32;
   const int grid = c.sm_count * (kSplatWarps == 4 ? 6 : 3) * 4;  // persistent: resident CTAs per SM x 4 rounds
   prof_begin(PK_SPLAT);
   const size_t smem = sizeof(float) * kSplatWarps * 32 * kWRec + (sizeof(unsigned short) + 1) * kSplatWarps * kWList;

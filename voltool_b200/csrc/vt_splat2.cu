@@ -1,0 +1,344 @@
+// vt_splat2.cu -- barrier-free splat: per-tile atom lists (one warp per tile) + per-region
+// accumulation (one warp per 8x8x4 region).  Same arithmetic and the same deterministic
+// accumulation order as the cooperative kernel in vt_sim.cu (group order, then lane order), but no
+// block barrier anywhere, so unevenly filled regions do not stall one another:
+//
+//   atom_box_kernel   per (pose, atom): the reference's truncated integer box, packed 3 x (lo|hi<<16)
+//   pose_bin_kernel   (vt_sim.cu) per (pose, group): tile bitmaps
+//   gather_kernel     warp per tile: walk the tile's group bitmap, test the 32 boxes of each group,
+//                     append id | region-mask << 24 to the tile's list in global memory (L2 resident)
+//   splat_list_kernel warp per (tile, region): filter the list by region bit, stage 32 atoms at a
+//                     time as separable records, accumulate 8 x-voxels per thread, write once
+//
+// A tile whose list would overflow its slot sets a flag; the caller then reruns the batch with the
+// cooperative kernel (no silent truncation).
+#include <cstdlib>
+#include <vector>
+
+#include "vt_pose.cuh"
+
+namespace vt {
+
+__device__ __forceinline__ float ex2_approx2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ int find_pose_tile(const PoseGeom *__restrict__ geo, int npose, int item) {
+  int lo = 0, hi = npose - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (geo[mid].tile_base <= item) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------ boxes
+__global__ void __launch_bounds__(256) atom_box_kernel(const PoseGeom *__restrict__ geo, int natoms,
+                                                       const float4 *__restrict__ tpos_all,
+                                                       const float4 *__restrict__ cst, float invgs,
+                                                       uint3 *__restrict__ boxes) {
+  const int p = blockIdx.y;
+  const PoseGeom &G = geo[p];
+  const float ox = G.org[0], oy = G.org[1], oz = G.org[2];
+  const int nv0 = G.nv[0], nv1 = G.nv[1], nv2 = G.nv[2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < natoms; i += gridDim.x * blockDim.x) {
+    const float4 a4 = tpos_all[(size_t)p * natoms + i];
+    const float rl = cst[i].z;
+    const float ax = a4.x - ox, ay = a4.y - oy, az = a4.z - oz;  // xyzr = pos - origin
+    float t = ax * invgs;
+    const int xmin = max(__float2int_rz(t - rl), 0), xmax = min(__float2int_rz(t + rl), nv0 - 1);
+    t = ay * invgs;
+    const int ymin = max(__float2int_rz(t - rl), 0), ymax = min(__float2int_rz(t + rl), nv1 - 1);
+    t = az * invgs;
+    const int zmin = max(__float2int_rz(t - rl), 0), zmax = min(__float2int_rz(t + rl), nv2 - 1);
+    uint3 b;
+    if (xmin > xmax || ymin > ymax || zmin > zmax) b = make_uint3(1u, 1u, 1u);  // lo 1 > hi 0: empty
+    else b = make_uint3((unsigned)xmin | ((unsigned)xmax << 16), (unsigned)ymin | ((unsigned)ymax << 16),
+                        (unsigned)zmin | ((unsigned)zmax << 16));
+    boxes[(size_t)p * natoms + i] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ gather
+constexpr int kGlist = 1024;  // hit groups expanded per round (32 bitmap words)
+
+__global__ void __launch_bounds__(128) gather_kernel(const PoseGeom *__restrict__ geo, const int *__restrict__ totals,
+                                                     int npose, int natoms, const unsigned int *__restrict__ bitmap,
+                                                     int tiles_cap, int nwords, const uint3 *__restrict__ boxes,
+                                                     unsigned int *__restrict__ tlist, int *__restrict__ tcount,
+                                                     int cap_t, int *__restrict__ overflow) {
+  __shared__ unsigned short s_gl[4][kGlist];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int lt = (1u << lane) - 1u;
+  const int total = totals[0];
+  const int nwarps = gridDim.x * 4;
+  for (int item = blockIdx.x * 4 + warp; item < total; item += nwarps) {
+    const int p = find_pose_tile(geo, npose, item);
+    const PoseGeom &G = geo[p];
+    const int local = item - G.tile_base;
+    const int tx = local % G.tiles[0], ty = (local / G.tiles[0]) % G.tiles[1], tz = local / (G.tiles[0] * G.tiles[1]);
+    const int x0 = tx * kTX, y0 = ty * kTY, z0 = tz * kTZ;
+    const unsigned int *__restrict__ bits = bitmap + ((size_t)p * tiles_cap + local) * nwords;
+    const uint3 *__restrict__ bx = boxes + (size_t)p * natoms;
+    unsigned int *__restrict__ out = tlist + ((size_t)p * tiles_cap + local) * cap_t;
+    int cnt = 0;
+    for (int w0 = 0; w0 < nwords; w0 += 32) {
+      // 32 words -> ordered list of set bits
+      unsigned int word = (w0 + lane < nwords) ? bits[w0 + lane] : 0u;
+      const int pc = __popc(word);
+      int incl = pc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int nhit = __shfl_sync(0xffffffffu, incl, 31);
+      int off = incl - pc;
+      while (word) {
+        const int bit = __ffs(word) - 1;
+        word &= word - 1;
+        s_gl[warp][off++] = (unsigned short)(lane * 32 + bit);
+      }
+      __syncwarp();
+      // one group per iteration, lane per atom; the next group's boxes are loaded one iteration ahead
+      uint3 nb = make_uint3(1u, 1u, 1u);
+      if (nhit > 0) {
+        const int id0 = (w0 * 32 + (int)s_gl[warp][0]) * 32 + lane;
+        if (id0 < natoms) nb = bx[id0];
+      }
+      for (int gi = 0; gi < nhit; ++gi) {
+        const int id = (w0 * 32 + (int)s_gl[warp][gi]) * 32 + lane;
+        const uint3 b = nb;
+        nb = make_uint3(1u, 1u, 1u);
+        if (gi + 1 < nhit) {
+          const int idn = (w0 * 32 + (int)s_gl[warp][gi + 1]) * 32 + lane;
+          if (idn < natoms) nb = bx[idn];
+        }
+        const int xmin = b.x & 0xffff, xmax = b.x >> 16, ymin = b.y & 0xffff, ymax = b.y >> 16;
+        const int zmin = b.z & 0xffff, zmax = b.z >> 16;
+        const bool take = id < natoms && xmin <= xmax && xmin <= x0 + kTX - 1 && xmax >= x0 && ymin <= y0 + kTY - 1 &&
+                          ymax >= y0 && zmin <= z0 + kTZ - 1 && zmax >= z0;
+        int mask = 0;
+        if (take) {
+          // bit w: box meets region w (x half w&1, z half (w>>1)&1, y block w>>2)
+          const int mx = (xmin <= x0 + 7 ? 1 : 0) | (xmax >= x0 + 8 ? 2 : 0);
+          const int mz = (zmin <= z0 + 3 ? 1 : 0) | (zmax >= z0 + 4 ? 2 : 0);
+#pragma unroll
+          for (int w = 0; w < kSplatWarps; ++w) {
+            const int yb = y0 + 8 * (w >> 2);
+            if (((mx >> (w & 1)) & 1) && ((mz >> ((w >> 1) & 1)) & 1) && ymin <= yb + 7 && ymax >= yb) mask |= 1 << w;
+          }
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, take);
+        if (take) {
+          const int slot = cnt + __popc(bal & lt);
+          if (slot < cap_t) out[slot] = (unsigned int)id | ((unsigned int)mask << 24);
+        }
+        cnt += __popc(bal);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      tcount[(size_t)p * tiles_cap + local] = cnt;
+      if (cnt > cap_t) atomicExch(overflow, 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ accumulate
+constexpr int kRec2 = 20;  // Ex[8] | dy^2[8] | dz^2[4]
+
+__global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__restrict__ geo,
+                                                            const int *__restrict__ totals, int npose, int natoms,
+                                                            const float4 *__restrict__ tpos_all,
+                                                            const float4 *__restrict__ cst,
+                                                            const uint3 *__restrict__ boxes,
+                                                            const unsigned int *__restrict__ tlist,
+                                                            const int *__restrict__ tcount, int cap_t, int tiles_cap,
+                                                            float gs, float *__restrict__ grid_all, long cap_grid) {
+  __shared__ __align__(16) float s_rec[4][32 * kRec2];
+  __shared__ float s_ar[4][32], s_rl2[4][32];
+  __shared__ int s_pend[4][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int lt = (1u << lane) - 1u;
+  const long ntask = (long)totals[0] * kSplatWarps;
+  const long stride = (long)gridDim.x * 4;
+  const int ly = lane & 7, lz = lane >> 3;
+  float *rec = s_rec[warp];
+  for (long task = (long)blockIdx.x * 4 + warp; task < ntask; task += stride) {
+    const int item = (int)(task / kSplatWarps), region = (int)(task - (long)item * kSplatWarps);
+    const int p = find_pose_tile(geo, npose, item);
+    const PoseGeom &G = geo[p];
+    const int local = item - G.tile_base;
+    const int tx = local % G.tiles[0], ty = (local / G.tiles[0]) % G.tiles[1], tz = local / (G.tiles[0] * G.tiles[1]);
+    const int nv0 = G.nv[0], nv1 = G.nv[1], nv2 = G.nv[2];
+    const float ox = G.org[0], oy = G.org[1], oz = G.org[2];
+    const int X0 = tx * kTX + (region & 1) * 8, Y0 = ty * kTY + (region >> 2) * 8, Z0 = tz * kTZ + ((region >> 1) & 1) * 4;
+    const float4 *__restrict__ tpos = tpos_all + (size_t)p * natoms;
+    const uint3 *__restrict__ bx = boxes + (size_t)p * natoms;
+    const unsigned int *__restrict__ list = tlist + ((size_t)p * tiles_cap + local) * cap_t;
+    const int n = min(tcount[(size_t)p * tiles_cap + local], cap_t);
+
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+
+    auto process = [&](int m) {
+      if (lane < m) {
+        const int id = s_pend[warp][lane];
+        const float4 a4 = tpos[id];
+        const float4 k4 = cst[id];
+        const uint3 b = bx[id];
+        const float ax = a4.x - ox, ay = a4.y - oy, az = a4.z - oz;  // xyzr = pos - origin
+        const float arinv = k4.x;
+        const int xmin = b.x & 0xffff, xmax = b.x >> 16, ymin = b.y & 0xffff, ymax = b.y >> 16;
+        const int zmin = b.z & 0xffff, zmax = b.z >> 16;
+        float *r = rec + lane * kRec2;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int X = X0 + k;
+          const float dx = (float)X * gs - ax;
+          const float e = ex2_approx2((dx * dx) * arinv);
+          v[k] = (X >= xmin && X <= xmax) ? e : 0.0f;
+        }
+        *reinterpret_cast<float4 *>(r) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(r + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int Y = Y0 + k;
+          const float dy = (float)Y * gs - ay;
+          v[k] = (Y >= ymin && Y <= ymax) ? dy * dy : INFINITY;
+        }
+        *reinterpret_cast<float4 *>(r + 8) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(r + 12) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int Z = Z0 + k;
+          const float dz = (float)Z * gs - az;
+          v[k] = (Z >= zmin && Z <= zmax) ? dz * dz : INFINITY;
+        }
+        *reinterpret_cast<float4 *>(r + 16) = make_float4(v[0], v[1], v[2], v[3]);
+        s_ar[warp][lane] = arinv;
+        s_rl2[warp][lane] = k4.y;
+      }
+      __syncwarp();
+      for (int a = 0; a < m; ++a) {
+        const float *r = rec + a * kRec2;
+        const float d2 = r[8 + ly] + r[16 + lz];               // dy*dy + dz*dz
+        const bool pass = d2 < s_rl2[warp][a];                 // !(dy2dz2 >= radlim2)
+        if (!__any_sync(0xffffffffu, pass)) continue;
+        const float e = pass ? ex2_approx2(d2 * s_ar[warp][a]) : 0.0f;
+        const float4 e0 = *reinterpret_cast<const float4 *>(r);
+        const float4 e1 = *reinterpret_cast<const float4 *>(r + 4);
+        acc[0] = __fmaf_rn(e0.x, e, acc[0]); acc[1] = __fmaf_rn(e0.y, e, acc[1]);
+        acc[2] = __fmaf_rn(e0.z, e, acc[2]); acc[3] = __fmaf_rn(e0.w, e, acc[3]);
+        acc[4] = __fmaf_rn(e1.x, e, acc[4]); acc[5] = __fmaf_rn(e1.y, e, acc[5]);
+        acc[6] = __fmaf_rn(e1.z, e, acc[6]); acc[7] = __fmaf_rn(e1.w, e, acc[7]);
+      }
+      __syncwarp();
+    };
+
+    int have = 0;
+    for (int b0 = 0; b0 < n; b0 += 32) {
+      const int i = b0 + lane;
+      const unsigned int e = i < n ? __ldg(list + i) : 0u;
+      const bool mine = i < n && ((e >> (24 + region)) & 1u);
+      const unsigned int bal = __ballot_sync(0xffffffffu, mine);
+      if (bal == 0u) continue;
+      if (mine) s_pend[warp][have + __popc(bal & lt)] = (int)(e & 0xffffffu);
+      have += __popc(bal);
+      __syncwarp();
+      if (have >= 32) {
+        process(32);
+        const int rest = have - 32;
+        const int keep = lane < rest ? s_pend[warp][32 + lane] : 0;
+        __syncwarp();
+        if (lane < rest) s_pend[warp][lane] = keep;
+        have = rest;
+        __syncwarp();
+      }
+    }
+    if (have > 0) process(have);
+
+    const int Y = Y0 + ly, Z = Z0 + lz;
+    if (Y < nv1 && Z < nv2) {
+      float *row = grid_all + (size_t)p * cap_grid + ((size_t)Z * nv1 + Y) * nv0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (X0 + k < nv0) row[X0 + k] = acc[k];
+    }
+  }
+}
+
+int batch_lists_overflowed(PoseBatch &pb, int *flag) {
+  Ctx &c = ctx();
+  int h[4];
+  VT_CUDA(cudaMemcpyAsync(h, pb.d_totals, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  VT_CUDA(cudaStreamSynchronize(c.stream));
+  *flag = h[2];
+  return 0;
+}
+
+// Size the per-tile lists from the pose(s) already prepared in pb: count-only gather on pose 0,
+// capacity = 1.6 x the fullest tile (rigid poses of one structure fill tiles alike); then allocate.
+int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  pb.use_lists = false;
+  if (getenv("VOLTOOL_SPLAT_COOP") || as.n >= (1 << 24) || pb.cap_n > 65535) return 0;
+  const int nwords = (as.ngroups + 31) / 32;
+  if (dev_alloc((void **)&pb.d_boxes, sizeof(uint3) * (size_t)pb.B * as.n)) return 2;
+  if (dev_alloc((void **)&pb.d_tcount, sizeof(int) * (size_t)pb.B * pb.tiles_cap)) return 2;
+  VT_CUDA(cudaMemsetAsync(pb.d_totals + 2, 0, sizeof(int), c.stream));
+  int rc = batch_bin(as, pb, 1);
+  if (rc) return rc;
+  int gx = (as.n + 255) / 256;
+  if (gx > 64) gx = 64;
+  atom_box_kernel<<<dim3(gx, 1), 256, 0, c.stream>>>(pb.d_geom, as.n, pb.d_tpos, as.d_const, as.prm.invgs, pb.d_boxes);
+  VT_LAUNCHED();
+  VT_CUDA(cudaMemsetAsync(pb.d_tcount, 0, sizeof(int) * (size_t)pb.tiles_cap, c.stream));
+  gather_kernel<<<c.sm_count * 8, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, 1, as.n, pb.d_bitmap, pb.tiles_cap, nwords,
+                                                      pb.d_boxes, nullptr, pb.d_tcount, 0, pb.d_totals + 3);
+  VT_LAUNCHED();
+  std::vector<int> cnt(pb.tiles_cap);
+  VT_CUDA(cudaMemcpyAsync(cnt.data(), pb.d_tcount, sizeof(int) * pb.tiles_cap, cudaMemcpyDeviceToHost, c.stream));
+  VT_CUDA(cudaStreamSynchronize(c.stream));
+  int mx = 0;
+  for (int v : cnt) mx = v > mx ? v : mx;
+  int cap = (int)(1.6 * mx) + 128;
+  cap = (cap + 127) & ~127;
+  const size_t bytes = sizeof(unsigned int) * (size_t)pb.B * pb.tiles_cap * cap;
+  if (bytes > ((size_t)12 << 30)) return 0;  // would not pay: keep the cooperative kernel
+  if (dev_alloc((void **)&pb.d_tlist, bytes)) return 2;
+  pb.cap_t = cap;
+  pb.use_lists = true;
+  return 0;
+}
+
+// returns 0 on launch; the overflow flag (d_totals[2]) must be checked by the caller after a sync
+int batch_splat_lists(const AtomSet &as, PoseBatch &pb, int npose) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  const int nwords = (as.ngroups + 31) / 32;
+  int gx = (as.n + 255) / 256;
+  if (gx > 64) gx = 64;
+  prof_begin(PK_SETUP);
+  atom_box_kernel<<<dim3(gx, npose), 256, 0, c.stream>>>(pb.d_geom, as.n, pb.d_tpos, as.d_const, as.prm.invgs, pb.d_boxes);
+  VT_LAUNCHED();
+  gather_kernel<<<c.sm_count * 8, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, pb.d_bitmap, pb.tiles_cap, nwords,
+                                                      pb.d_boxes, pb.d_tlist, pb.d_tcount, pb.cap_t, pb.d_totals + 2);
+  prof_end(PK_SETUP);
+  VT_LAUNCHED();
+  prof_begin(PK_SPLAT);
+  splat_list_kernel<<<c.sm_count * 6 * 4, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, pb.d_tpos, as.d_const,
+                                                              pb.d_boxes, pb.d_tlist, pb.d_tcount, pb.cap_t, pb.tiles_cap,
+                                                              as.prm.gs, pb.d_grid, pb.cap_grid);
+  prof_end(PK_SPLAT);
+  VT_LAUNCHED();
+  return 0;
+}
+
+}  // namespace vt
