@@ -195,7 +195,7 @@ def run_ours(args):
     ms_total = timed(step_resident, W, K)
     clocks = sampler.stop() if rank == 0 else None
     launches = vt.launch_count() - launches0 + 2 * K   # + torch max / copy per step
-    prof = {k: vt.profile_get(k) for k in ("transform", "splat", "pose_cc")}
+    prof = {k: vt.profile_get(k) for k in ("transform", "setup", "splat", "pose_cc")}
     vt.profile_enable(False)
     value = world * P * K / (ms_total * 1e-3)
     best = gathered.cpu().numpy().reshape(world, 2)

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128) gather_kernel(const PoseGeom *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------ accumulate
-constexpr int kRec2 = 20;  // Ex[8] | dy^2[8] | dz^2[4]
+constexpr int kRec2 = 24;  // Ex[8] | dy^2[8] | dz^2[4] | arinv, radlim^2, pad, pad
 
 __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__restrict__ geo,
                                                             const int *__restrict__ totals, int npose, int natoms,
@@ -159,7 +159,6 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
                                                             const int *__restrict__ tcount, int cap_t, int tiles_cap,
                                                             float gs, float *__restrict__ grid_all, long cap_grid) {
   __shared__ __align__(16) float s_rec[4][32 * kRec2];
-  __shared__ float s_ar[4][32], s_rl2[4][32];
   __shared__ int s_pend[4][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int lt = (1u << lane) - 1u;
@@ -221,30 +220,37 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
           v[k] = (Z >= zmin && Z <= zmax) ? dz * dz : INFINITY;
         }
         *reinterpret_cast<float4 *>(r + 16) = make_float4(v[0], v[1], v[2], v[3]);
-        s_ar[warp][lane] = arinv;
-        s_rl2[warp][lane] = k4.y;
+        *reinterpret_cast<float4 *>(r + 20) = make_float4(arinv, k4.y, 0.f, 0.f);
       }
       __syncwarp();
-      for (int a = 0; a < m; ++a) {
-        const float *r = rec + a * kRec2;
-        const float d2 = r[8 + ly] + r[16 + lz];               // dy*dy + dz*dz
-        const bool pass = d2 < s_rl2[warp][a];                 // !(dy2dz2 >= radlim2)
-        if (!__any_sync(0xffffffffu, pass)) continue;
-        const float e = pass ? ex2_approx2(d2 * s_ar[warp][a]) : 0.0f;
+      // branch-free: a staged atom whose disc misses every lane just adds zeros (rare: its box already
+      // meets this region).  Two atoms per trip so their shared-memory loads overlap.
+      auto visit = [&](const float *r) {
+        const float d2 = r[8 + ly] + r[16 + lz];                                  // dy*dy + dz*dz
+        const float2 c2 = *reinterpret_cast<const float2 *>(r + 20);              // arinv, radlim^2
+        const float e = (d2 < c2.y) ? ex2_approx2(d2 * c2.x) : 0.0f;              // !(dy2dz2 >= radlim2)
         const float4 e0 = *reinterpret_cast<const float4 *>(r);
         const float4 e1 = *reinterpret_cast<const float4 *>(r + 4);
         acc[0] = __fmaf_rn(e0.x, e, acc[0]); acc[1] = __fmaf_rn(e0.y, e, acc[1]);
         acc[2] = __fmaf_rn(e0.z, e, acc[2]); acc[3] = __fmaf_rn(e0.w, e, acc[3]);
         acc[4] = __fmaf_rn(e1.x, e, acc[4]); acc[5] = __fmaf_rn(e1.y, e, acc[5]);
         acc[6] = __fmaf_rn(e1.z, e, acc[6]); acc[7] = __fmaf_rn(e1.w, e, acc[7]);
+      };
+      int a = 0;
+      for (; a + 2 <= m; a += 2) {
+        visit(rec + a * kRec2);
+        visit(rec + (a + 1) * kRec2);
       }
+      if (a < m) visit(rec + a * kRec2);
       __syncwarp();
     };
 
     int have = 0;
+    unsigned int e_next = lane < n ? __ldg(list + lane) : 0u;  // the list is read one chunk ahead
     for (int b0 = 0; b0 < n; b0 += 32) {
       const int i = b0 + lane;
-      const unsigned int e = i < n ? __ldg(list + i) : 0u;
+      const unsigned int e = e_next;
+      e_next = (i + 32 < n) ? __ldg(list + i + 32) : 0u;
       const bool mine = i < n && ((e >> (24 + region)) & 1u);
       const unsigned int bal = __ballot_sync(0xffffffffu, mine);
       if (bal == 0u) continue;
