@@ -5,8 +5,7 @@
 // source map a thread keeps the bilinear (x then y) value of the two source planes it is between;
 // stepping z by one usually turns the upper plane into the lower one, so only one new plane is
 // sampled per step.  Within a plane, source rows shared by neighbouring output rows are x-lerped
-// once, and the x+1 neighbour comes from the next lane by shuffle when the tables say it is the
-// same voxel (a predicated load otherwise).  Every value is produced by the reference's expression
+// once.  Every value is produced by the reference's expression
 // (voxel_value_interpolate, VolumetricData.C:264-291): a0 + xf*(a1-a0), then y, then z.
 #pragma once
 #include "vt_device.cuh"
@@ -24,7 +23,6 @@ struct MapMarch {
   // per thread (x)
   int x0, x1;
   float xf;
-  bool x1_from_next;  // lane+1 holds this lane's x1 voxel in its x0
   unsigned int loadmask;  // bit 2r: row r0[r] must be loaded, bit 2r+1: row r1[r] (else reuse)
   // per output row (warp-uniform)
   int r0[Y], r1[Y];   // row offsets inside a plane (< 2^31 voxels per plane)
@@ -40,8 +38,6 @@ __device__ __forceinline__ void march_init(MapMarch<Y> &m, const float *d, int n
   m.d = d;
   m.pstride = (long)nx_src * ny_src;
   m.x0 = ex.i0; m.x1 = ex.i1; m.xf = ex.f;
-  const int nx0 = __shfl_down_sync(0xffffffffu, m.x0, 1);
-  m.x1_from_next = ((threadIdx.x & 31) < 31) && (nx0 == m.x1);
 #pragma unroll
   for (int r = 0; r < Y; ++r) {
     const int gy = min(gy0 + r, ny_out - 1);
@@ -59,44 +55,28 @@ __device__ __forceinline__ void march_init(MapMarch<Y> &m, const float *d, int n
   m.z0 = -1; m.z1 = -1;
 }
 
-// Bilinear values of plane z for the Y rows.  All loads of the plane are issued before the first
-// shuffle consumes one (a shuffle is the first use of a load: interleaving them would serialise
-// the memory latencies).  Which rows need loading is warp-uniform (m.loadmask).
+// Bilinear values of plane z for the Y rows.  Both x neighbours are plain loads (they share a
+// sector almost always; L1 serves the second): a shuffle would save the request but costs a
+// WARPSYNC/collective pair per row in SASS.  All loads of the plane are issued before the first
+// lerp; which rows need loading is warp-uniform (m.loadmask).
 template <int Y>
 __device__ __forceinline__ void march_plane(const MapMarch<Y> &m, int z, float (&out)[Y]) {
-  const float *__restrict__ P = m.d + (long)z * m.pstride;
+  const float *__restrict__ P0 = m.d + (long)z * m.pstride + m.x0;
+  const float *__restrict__ P1 = m.d + (long)z * m.pstride + m.x1;
   float a0[Y], a1[Y], b0[Y], b1[Y];
 #pragma unroll
   for (int r = 0; r < Y; ++r) {
     a0[r] = a1[r] = b0[r] = b1[r] = 0.f;
-    if ((m.loadmask >> (2 * r)) & 1) a0[r] = __ldg(P + m.r0[r] + m.x0);
-    if ((m.loadmask >> (2 * r + 1)) & 1) b0[r] = __ldg(P + m.r1[r] + m.x0);
-  }
-  if (!m.x1_from_next) {  // lanes whose x+1 neighbour is not the next lane's voxel
-#pragma unroll
-    for (int r = 0; r < Y; ++r) {
-      if ((m.loadmask >> (2 * r)) & 1) a1[r] = __ldg(P + m.r0[r] + m.x1);
-      if ((m.loadmask >> (2 * r + 1)) & 1) b1[r] = __ldg(P + m.r1[r] + m.x1);
-    }
+    if ((m.loadmask >> (2 * r)) & 1) { a0[r] = __ldg(P0 + m.r0[r]); a1[r] = __ldg(P1 + m.r0[r]); }
+    if ((m.loadmask >> (2 * r + 1)) & 1) { b0[r] = __ldg(P0 + m.r1[r]); b1[r] = __ldg(P1 + m.r1[r]); }
   }
   float prev_xl = 0.f;
 #pragma unroll
   for (int r = 0; r < Y; ++r) {
-    float xa, xb;
-    if ((m.loadmask >> (2 * r)) & 1) {
-      const float t = __shfl_down_sync(0xffffffffu, a0[r], 1);
-      const float v1 = m.x1_from_next ? t : a1[r];
-      xa = a0[r] + m.xf * (v1 - a0[r]);
-    } else {
-      xa = prev_xl;  // same source row as the previous output row's upper row
-    }
-    if ((m.loadmask >> (2 * r + 1)) & 1) {
-      const float t = __shfl_down_sync(0xffffffffu, b0[r], 1);
-      const float v1 = m.x1_from_next ? t : b1[r];
-      xb = b0[r] + m.xf * (v1 - b0[r]);
-    } else {
-      xb = xa;       // clamped edge: both rows are the same source row
-    }
+    // same source row as the previous output row's upper row -> reuse its x lerp
+    const float xa = ((m.loadmask >> (2 * r)) & 1) ? a0[r] + m.xf * (a1[r] - a0[r]) : prev_xl;
+    // clamped edge: both rows are the same source row
+    const float xb = ((m.loadmask >> (2 * r + 1)) & 1) ? b0[r] + m.xf * (b1[r] - b0[r]) : xa;
     prev_xl = xb;
     out[r] = xa + m.yf[r] * (xb - xa);
   }
