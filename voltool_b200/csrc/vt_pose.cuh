@@ -48,7 +48,8 @@ struct AtomSet {
   int n = 0, ngroups = 0;
   float4 *d_xyzr = nullptr;   // origin-frame coordinates + radius (sorted order)
   float4 *d_const = nullptr;  // per atom: arinv, radlim^2, radlim/gs, radius
-  float4 *d_group = nullptr;  // per group: centre (origin frame) + reach
+  float4 *d_group = nullptr;  // per group: centre (origin frame) + bounding-sphere radius
+  float *d_gcut = nullptr;    // per group: largest cutoff (gausslim * sigma) of its atoms
   int *h_perm = nullptr;      // sorted position -> caller's atom index (host)
   float *h_radii = nullptr;   // radii in the caller's order (host)
   float maxrad = 0.f, pad = 0.f;

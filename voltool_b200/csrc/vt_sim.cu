@@ -58,8 +58,10 @@ static inline unsigned int spread10(unsigned int v) {
   return v;
 }
 
-static void group_spheres(const AtomSet &as, const std::vector<float4> &xyzr, std::vector<float4> &groups) {
+static void group_spheres(const AtomSet &as, const std::vector<float4> &xyzr, std::vector<float4> &groups,
+                          std::vector<float> &cuts) {
   groups.resize(as.ngroups);
+  cuts.resize(as.ngroups);
   for (int g = 0; g < as.ngroups; ++g) {
     const int a0 = g * 32, a1 = std::min(as.n, a0 + 32);
     float lo[3] = {xyzr[a0].x, xyzr[a0].y, xyzr[a0].z}, hi[3] = {lo[0], lo[1], lo[2]};
@@ -75,10 +77,12 @@ static void group_spheres(const AtomSet &as, const std::vector<float4> &xyzr, st
       const float dx = xyzr[i].x - c[0], dy = xyzr[i].y - c[1], dz = xyzr[i].z - c[2];
       r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
     }
-    // reach = sphere radius + the farthest voxel an atom touches + slack for float rounding of the
-    // rigid transform.  The footprint is a box in x and a disc in y-z (radius gausslim*sigma each),
-    // so its far corner sits sqrt(2) cutoffs from the atom.
-    const float reach = std::sqrt(r2) + 1.41422f * maxcut + 0.05f + 1e-4f * (std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]));
+    // w = bounding-sphere radius + slack for float rounding of the rigid transform.  The largest
+    // cutoff of the group is kept separately: an atom's footprint is a box in x and a disc in y-z,
+    // both inside the cube of half-width cutoff, so "sphere(radius) meets tile box grown by cutoff"
+    // is a tighter conservative test than one sphere of radius + sqrt(2)*cutoff.
+    const float reach = std::sqrt(r2) + 0.05f + 1e-4f * (std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]));
+    cuts[g] = maxcut;
     groups[g] = make_float4(c[0], c[1], c[2], reach);
   }
 }
@@ -90,7 +94,8 @@ static int upload_positions(AtomSet &as, const float *pos, const float *radii_so
     xyzr[i] = make_float4(pos[3 * o], pos[3 * o + 1], pos[3 * o + 2], radii_sorted_src[o]);
   }
   std::vector<float4> groups;
-  group_spheres(as, xyzr, groups);
+  std::vector<float> cuts;
+  group_spheres(as, xyzr, groups, cuts);
   // bounding sphere of everything (capacity planning)
   double c[3] = {0, 0, 0};
   for (int i = 0; i < as.n; ++i) { c[0] += xyzr[i].x; c[1] += xyzr[i].y; c[2] += xyzr[i].z; }
@@ -104,6 +109,7 @@ static int upload_positions(AtomSet &as, const float *pos, const float *radii_so
   cudaStream_t s = ctx().stream;
   VT_CUDA(cudaMemcpyAsync(as.d_xyzr, xyzr.data(), sizeof(float4) * as.n, cudaMemcpyHostToDevice, s));
   VT_CUDA(cudaMemcpyAsync(as.d_group, groups.data(), sizeof(float4) * as.ngroups, cudaMemcpyHostToDevice, s));
+  VT_CUDA(cudaMemcpyAsync(as.d_gcut, cuts.data(), sizeof(float) * as.ngroups, cudaMemcpyHostToDevice, s));
   if (first) {
     std::vector<float4> cst(as.n);
     const float invgs = as.prm.invgs;
@@ -157,13 +163,14 @@ int atomset_create(const float *pos, const float *radii, long n, const SimParams
   if (dev_alloc((void **)&as.d_xyzr, sizeof(float4) * n)) return 2;
   if (dev_alloc((void **)&as.d_const, sizeof(float4) * n)) return 2;
   if (dev_alloc((void **)&as.d_group, sizeof(float4) * as.ngroups)) return 2;
+  if (dev_alloc((void **)&as.d_gcut, sizeof(float) * as.ngroups)) return 2;
   return upload_positions(as, pos, radii, true);
 }
 
 int atomset_set_positions(AtomSet &as, const float *pos) { return upload_positions(as, pos, as.h_radii, false); }
 
 void atomset_destroy(AtomSet &as) {
-  dev_free(as.d_xyzr); dev_free(as.d_const); dev_free(as.d_group);
+  dev_free(as.d_xyzr); dev_free(as.d_const); dev_free(as.d_group); dev_free(as.d_gcut);
   delete[] as.h_perm;
   delete[] as.h_radii;
   as = AtomSet();
@@ -430,7 +437,8 @@ constexpr int kWList = kWGroups * 32;  // per-warp gathered atoms per batch
 // reaches in a per-tile bitmap (atomicOr: the result does not depend on the order).  The splat
 // kernel then walks set bits in index order, so its accumulation order stays deterministic.
 __global__ void __launch_bounds__(256) pose_bin_kernel(const PoseGeom *__restrict__ geo, int ngroups,
-                                                       const float4 *__restrict__ tgroup_all, float gs, float invgs,
+                                                       const float4 *__restrict__ tgroup_all,
+                                                       const float *__restrict__ gcut, float gs, float invgs,
                                                        unsigned int *__restrict__ bitmap, int tiles_cap, int nwords) {
   const int p = blockIdx.y;
   const PoseGeom &G = geo[p];
@@ -439,7 +447,8 @@ __global__ void __launch_bounds__(256) pose_bin_kernel(const PoseGeom *__restric
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
     const float4 c = tgroup_all[(size_t)p * ngroups + g];
     const float rx = (c.x - G.org[0]) * invgs, ry = (c.y - G.org[1]) * invgs, rz = (c.z - G.org[2]) * invgs;
-    const float rr = c.w * invgs + 2.0f;  // reach in voxels + slack; the exact test below decides
+    const float cut = gcut[g];
+    const float rr = (c.w + cut) * invgs + 2.0f;  // reach in voxels + slack; the exact test below decides
     const int tx0 = max(0, (int)floorf((rx - rr) / kTX) - 1), tx1 = min(ntx - 1, (int)floorf((rx + rr) / kTX) + 1);
     const int ty0 = max(0, (int)floorf((ry - rr) / kTY) - 1), ty1 = min(nty - 1, (int)floorf((ry + rr) / kTY) + 1);
     const int tz0 = max(0, (int)floorf((rz - rr) / kTZ) - 1), tz1 = min(ntz - 1, (int)floorf((rz + rr) / kTZ) + 1);
@@ -448,9 +457,9 @@ __global__ void __launch_bounds__(256) pose_bin_kernel(const PoseGeom *__restric
         for (int tx = tx0; tx <= tx1; ++tx) {
           // tile box in cartesian space with one voxel of slack for the integer truncations
           const int x0 = tx * kTX, y0 = ty * kTY, z0 = tz * kTZ;
-          const float bx0 = G.org[0] + (x0 - 1) * gs, bx1 = G.org[0] + (x0 + kTX) * gs;
-          const float by0 = G.org[1] + (y0 - 1) * gs, by1 = G.org[1] + (y0 + kTY) * gs;
-          const float bz0 = G.org[2] + (z0 - 1) * gs, bz1 = G.org[2] + (z0 + kTZ) * gs;
+          const float bx0 = G.org[0] + (x0 - 1) * gs - cut, bx1 = G.org[0] + (x0 + kTX) * gs + cut;
+          const float by0 = G.org[1] + (y0 - 1) * gs - cut, by1 = G.org[1] + (y0 + kTY) * gs + cut;
+          const float bz0 = G.org[2] + (z0 - 1) * gs - cut, bz1 = G.org[2] + (z0 + kTZ) * gs + cut;
           const float dx = fmaxf(fmaxf(bx0 - c.x, 0.0f), c.x - bx1);
           const float dy = fmaxf(fmaxf(by0 - c.y, 0.0f), c.y - by1);
           const float dz = fmaxf(fmaxf(bz0 - c.z, 0.0f), c.z - bz1);
@@ -685,7 +694,7 @@ int batch_bin(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_CUDA(cudaMemsetAsync(pb.d_bitmap, 0, sizeof(unsigned int) * (size_t)npose * pb.tiles_cap * nwords, c.stream));
   int gx = (as.ngroups + 255) / 256;
   if (gx > 32) gx = 32;
-  pose_bin_kernel<<<dim3(gx, npose), 256, 0, c.stream>>>(pb.d_geom, as.ngroups, pb.d_tgroup, as.prm.gs, as.prm.invgs,
+  pose_bin_kernel<<<dim3(gx, npose), 256, 0, c.stream>>>(pb.d_geom, as.ngroups, pb.d_tgroup, as.d_gcut, as.prm.gs, as.prm.invgs,
                                                           pb.d_bitmap, pb.tiles_cap, nwords);
   prof_end(PK_SETUP);
   VT_LAUNCHED();
