@@ -87,23 +87,58 @@ __global__ void __launch_bounds__(96) com_tables_kernel(const float *__restrict_
   }
 }
 
-// pass 2: one warp.  Lanes 0..2 own the accumulators and take the O(1) table step when they can;
-// when any of them has to replay a chunk, all 32 lanes first rebuild that chunk's addends in shared
-// memory (coalesced loads, parallel coordinate arithmetic) and the owning lane then does only the
-// dependent float adds.
-__global__ void __launch_bounds__(32) com_walk_kernel(const float *__restrict__ d, long n, DevCoord c, int L,
-                                                      long nchunks, const ComEntry *__restrict__ tab,
-                                                      const int *__restrict__ emin, float *__restrict__ out,
-                                                      int *__restrict__ replayed) {
+// pass 2: one CTA of 8 warps.  Lanes 0..2 of warp 0 own the accumulators and take the O(1) table
+// step when they can; when any of them has to replay a chunk, all 256 threads first rebuild that
+// chunk's addends in shared memory (coalesced loads, parallel coordinate arithmetic) and the owning
+// lane then does only the dependent float adds.
+constexpr int kWalkThreads = 256;
+
+__global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__restrict__ d, long n, DevCoord c, int L,
+                                                               long nchunks, const ComEntry *__restrict__ tab,
+                                                               const int *__restrict__ emin, float *__restrict__ out,
+                                                               int *__restrict__ replayed) {
   extern __shared__ float s_a[];  // [3][L]
-  const int lane = threadIdx.x;
-  const int k = lane < 3 ? lane : 0;
+  __shared__ unsigned int s_need;   // which accumulators replay the chunk in s_chunk (0xffffffff: exit)
+  __shared__ long s_chunk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long nxy = (long)c.nx * c.ny;
+
+  // all threads: rebuild the addends of one chunk for the accumulators in `need`
+  auto stage = [&](long chunk, unsigned int need) {
+    const long base = chunk * L;
+    const int cnt = (int)((n - base) < L ? (n - base) : L);
+    for (int i = tid; i < cnt; i += kWalkThreads) {
+      const long idx = base + i;
+      const int gz = (int)(idx / nxy);
+      const long r = idx - (long)gz * nxy;
+      const int gy = (int)(r / c.nx), gx = (int)(r - (long)gy * c.nx);
+      const float m = d[idx];
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk)
+        if ((need >> kk) & 1) s_a[kk * L + i] = com_addend(c, kk, m, gx, gy, gz);
+    }
+  };
+
+  if (warp != 0) {
+    // helper warps sleep on barrier 1 until warp 0 posts a chunk to replay (or the exit command);
+    // the table fast path of warp 0 involves no barrier at all
+    while (true) {
+      asm volatile("bar.sync 1, %0;" ::"r"(kWalkThreads));
+      const unsigned int need = s_need;
+      if (need == 0xffffffffu) break;
+      stage(s_chunk, need);
+      asm volatile("bar.sync 2, %0;" ::"r"(kWalkThreads));
+    }
+    return;
+  }
+
+  const bool owner = lane < 3;
+  const int k = owner ? lane : 0;
   float s = 0.0f;
   int nreplay = 0;
-  const long nxy = (long)c.nx * c.ny;
   for (long chunk = 0; chunk < nchunks; ++chunk) {
     bool replay = false;
-    if (lane < 3) {
+    if (owner) {
       const int e0 = emin[chunk * 3 + k];
       if (e0 != -100000) {  // else: nothing to add
         replay = true;
@@ -138,21 +173,15 @@ __global__ void __launch_bounds__(32) com_walk_kernel(const float *__restrict__ 
     }
     const unsigned int need = __ballot_sync(0xffffffffu, replay);
     if (need == 0u) continue;
-    const long base = chunk * L;
-    const int cnt = (int)((n - base) < L ? (n - base) : L);
-    for (int i = lane; i < cnt; i += 32) {
-      const long idx = base + i;
-      const int gz = (int)(idx / nxy);
-      const long r = idx - (long)gz * nxy;
-      const int gy = (int)(r / c.nx), gx = (int)(r - (long)gy * c.nx);
-      const float m = d[idx];
-#pragma unroll
-      for (int kk = 0; kk < 3; ++kk)
-        if ((need >> kk) & 1) s_a[kk * L + i] = com_addend(c, kk, m, gx, gy, gz);
-    }
+    if (lane == 0) { s_need = need; s_chunk = chunk; }
     __syncwarp();
+    asm volatile("bar.sync 1, %0;" ::"r"(kWalkThreads));
+    stage(chunk, need);
+    asm volatile("bar.sync 2, %0;" ::"r"(kWalkThreads));
     if (replay) {
       ++nreplay;
+      const long base = chunk * L;
+      const int cnt = (int)((n - base) < L ? (n - base) : L);
       const float *a = s_a + k * L;
       int i = 0;
       for (; i + 16 <= cnt; i += 16) {  // loads batched ahead of the dependent add chain
@@ -167,7 +196,10 @@ __global__ void __launch_bounds__(32) com_walk_kernel(const float *__restrict__ 
     }
     __syncwarp();
   }
-  if (lane < 3) {
+  if (lane == 0) s_need = 0xffffffffu;
+  __syncwarp();
+  asm volatile("bar.sync 1, %0;" ::"r"(kWalkThreads));
+  if (owner) {
     out[lane] = s;
     replayed[lane] = nreplay;
   }
@@ -203,7 +235,7 @@ int k_vol_com(const vt_map *m, double out[4]) {
   VT_LAUNCHED();
   if (smem > 48 * 1024)
     VT_CUDA(cudaFuncSetAttribute(com_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  com_walk_kernel<<<1, 32, smem, c.stream>>>(m->d, n, dc, L, nchunks, tab, emin, d_out, (int *)(d_out + 4));
+  com_walk_kernel<<<1, kWalkThreads, smem, c.stream>>>(m->d, n, dc, L, nchunks, tab, emin, d_out, (int *)(d_out + 4));
   prof_end(PK_STATS);
   VT_LAUNCHED();
   float h[8];
