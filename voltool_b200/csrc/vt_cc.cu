@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 2) cc_sep_kernel(DevMap A, DevMap B,
     const int xb = (int)(w % xtiles);
     const long r = w / xtiles;
     const int yg = (int)(r % ygroups), zc = (int)(r / ygroups);
-    cc_march_item(A.d, A.nx, A.ny, B.d, B.nx, B.ny, T + offAx, T + offAy, T + offAz, T + offBx, T + offBy, T + offBz, nx,
+    cc_march_item<kRows>(A.d, A.nx, A.ny, B.d, B.nx, B.ny, T + offAx, T + offAy, T + offAz, T + offBx, T + offBy, T + offBz, nx,
                   ny, xb * 32 + lane, yg * kRows, zc * kZChunk, min(nz, (zc + 1) * kZChunk), thr_f, a);
   }
   double acc[6] = {a.s[0], a.s[1], a.s[2], a.s[3], a.s[4], (double)a.n};

@@ -25,6 +25,7 @@ constexpr int kChunk = 64;     // atoms staged per compute round
 constexpr int kRec = 44;       // floats per staged atom record
 constexpr int kMaxIds = 2048;  // gathered atom ids per flush
 constexpr int kZChunkFit = 32;
+constexpr int kRowsFit = 4;     // output rows per thread in the batched cc kernel
 
 // per-pose geometry, written by pose_setup_kernel
 struct PoseGeom {

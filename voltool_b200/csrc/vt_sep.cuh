@@ -119,6 +119,7 @@ struct CcAcc {
 
 // One warp work item: 32 x, kRows y, output z in [zbeg, zend).  Tables: tA*/tB* per axis.
 // Adds this thread's voxels to its double partial sums.
+template <int Y>
 __device__ __forceinline__ void cc_march_item(const float *__restrict__ A, int anx, int any, const float *__restrict__ B,
                                               int bnx, int bny, const AxisEntry *__restrict__ tAx,
                                               const AxisEntry *__restrict__ tAy, const AxisEntry *__restrict__ tAz,
@@ -127,13 +128,13 @@ __device__ __forceinline__ void cc_march_item(const float *__restrict__ A, int a
                                               int zbeg, int zend, float thr_f, CcAcc &acc) {
   const int gxc = min(gx, nx - 1);
   const AxisEntry ax = tAx[gxc], bx = tBx[gxc];
-  MapMarch<kRows> ma, mb;
+  MapMarch<Y> ma, mb;
   march_init(ma, A, anx, any, ax, tAy, gy0, ny);
   march_init(mb, B, bnx, bny, bx, tBy, gy0, ny);
-  bool ok[kRows];
+  bool ok[Y];
   bool any_ok = false;
 #pragma unroll
-  for (int r = 0; r < kRows; ++r) {
+  for (int r = 0; r < Y; ++r) {
     const int gy = gy0 + r;
     const int gyc = min(gy, ny - 1);
     ok[r] = gx < nx && gy < ny && ax.inside && bx.inside && tAy[gyc].inside && tBy[gyc].inside;
@@ -143,12 +144,12 @@ __device__ __forceinline__ void cc_march_item(const float *__restrict__ A, int a
   for (int gz = zbeg; gz < zend; ++gz) {
     const AxisEntry az = tAz[gz], bz = tBz[gz];
     if (!az.inside || !bz.inside) continue;  // warp-uniform
-    float va[kRows], vb[kRows];
+    float va[Y], vb[Y];
     march_sample(ma, az, va);
-    bool want[kRows];
+    bool want[Y];
     bool any_want = false;
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
+    for (int r = 0; r < Y; ++r) {
       want[r] = ok[r] && (va[r] == va[r]) && (va[r] >= thr_f);   // !isnan(vA) && vA >= thr (MDFF.C:73-77)
       any_want |= want[r];
     }
@@ -156,7 +157,7 @@ __device__ __forceinline__ void cc_march_item(const float *__restrict__ A, int a
     march_sample(mb, bz, vb);
     int cnt = 0;
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
+    for (int r = 0; r < Y; ++r) {
       const bool take = want[r] && (vb[r] == vb[r]);
       if (take) {  // MDFF.C:78-83: double sums of float terms (float products)
         acc.s[0] += (double)va[r]; acc.s[1] += (double)vb[r];

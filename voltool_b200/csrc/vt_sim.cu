@@ -195,7 +195,7 @@ int batch_create(const AtomSet &as, const vt_grid *target, int B, PoseBatch &pb)
       maxlen = std::max(maxlen, std::min(la[k], (double)pb.cap_n * gs));
     }
     pb.cap_o = (int)(maxlen * dens * 1.01) + 8;
-    pb.cap_items = (long)((pb.cap_o + 31) / 32) * pb.cap_o * ((pb.cap_o + kZChunkFit - 1) / kZChunkFit);
+    pb.cap_items = (long)((pb.cap_o + 31) / 32) * ((pb.cap_o + kRowsFit - 1) / kRowsFit) * ((pb.cap_o + kZChunkFit - 1) / kZChunkFit);
   } else {
     pb.cap_o = 0;
     pb.cap_items = 0;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) pose_setup_kernel(const unsigned int *__r
         G.od[0] = xd[0]; G.od[1] = yd[1]; G.od[2] = zd[2];
         G.cc_xt = (og.xsize + 31) / 32;
         G.cc_zc = (og.zsize + kZChunkFit - 1) / kZChunkFit;
-        G.cc_items = G.cc_xt * ((og.ysize + kRows - 1) / kRows) * G.cc_zc;
+        G.cc_items = G.cc_xt * ((og.ysize + kRowsFit - 1) / kRowsFit) * G.cc_zc;
       }
     }
     out[p] = G;
@@ -738,15 +738,15 @@ __global__ void __launch_bounds__(256, 2) pose_cc_kernel(const PoseGeom *__restr
     const int local = item - G.cc_base;
     const int xb = local % G.cc_xt;
     const int r = local / G.cc_xt;
-    const int ygroups = (G.no[1] + kRows - 1) / kRows;
+    const int ygroups = (G.no[1] + kRowsFit - 1) / kRowsFit;
     const int yg = r % ygroups, zc = r / ygroups;
     const geom::AxisEntry *__restrict__ T = tab_all + (size_t)p * 6 * cap_o;
     CcAcc a;
 #pragma unroll
     for (int k = 0; k < 5; ++k) a.s[k] = 0.0;
     a.n = 0;
-    cc_march_item(grid_all + (size_t)p * cap_grid, G.nv[0], G.nv[1], tdata, tnx, tny, T, T + cap_o, T + 2 * cap_o,
-                  T + 3 * cap_o, T + 4 * cap_o, T + 5 * cap_o, G.no[0], G.no[1], xb * 32 + lane, yg * kRows,
+    cc_march_item<kRowsFit>(grid_all + (size_t)p * cap_grid, G.nv[0], G.nv[1], tdata, tnx, tny, T, T + cap_o, T + 2 * cap_o,
+                  T + 3 * cap_o, T + 4 * cap_o, T + 5 * cap_o, G.no[0], G.no[1], xb * 32 + lane, yg * kRowsFit,
                   zc * kZChunkFit, min(G.no[2], (zc + 1) * kZChunkFit), thr_f, a);
     double v[6] = {a.s[0], a.s[1], a.s[2], a.s[3], a.s[4], (double)a.n};
 #pragma unroll
