@@ -256,6 +256,16 @@ def run_ours(args):
            "gpu_launches": int(launches), "roofline": roofline,
            "best_of_last_step": {"cc": float(best[:, 0].max()), "planted_deg": PLANTED}}
 
+    if world == 1 and not args.no_extras:
+        # the reference's own workload: one full `voltool fit` (COM alignment, 3375 + 432 + 128 candidates,
+        # skip-rule replay) through the C ABI with host buffers
+        vt.sync()
+        t0 = time.perf_counter()
+        p_fit, fres = vt.fit(pos, radii, mass, tmap, RESOLUTION)
+        dt = time.perf_counter() - t0
+        out["fit_call"] = {"seconds": dt, "candidates_computed": int(fres.n_computed),
+                           "candidates_visited_by_reference_loop": int(fres.n_evaluated), "best_cc": float(fres.best_cc),
+                           "stage_best": list(fres.stage_best), "note": "vt_fit incl. vol_com on the 256^3 target"}
     if world == 1:
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(pos, radii, com, tmap, poses, budget_s=args.cpu_budget)
