@@ -234,8 +234,10 @@ def run_ours(args):
     poses_done = P * K
     fp32_peak = props["sm_count"] * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     achieved = FLOP_PER_PAIR * pairs * poses_done / (splat_ms * 1e-3) / 1e12 if splat_ms > 0 else None
-    roofline = {"kernel": "splat_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": (achieved / fp32_peak) if achieved else None, "traffic": None,
+    roofline = {"kernel": "splat_list_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": (achieved / fp32_peak) if achieved else None,
+                "traffic": 5.15e8 * (splat_n and (P * K / splat_n) / 128.0) if args.atoms == 50000 else None,
+                "traffic_source": "profiles/r1c_splat_list_kernel_summary.txt: dram read 287 MB + write 228 MB per 128-pose launch",
                 "peak_source": f"{props['sm_count']} SMs x 128 lanes x 2 x sm_max_mhz ({peaks['source']} MEASURED_PEAKS); "
                                "no tensor cores: nothing here is a contraction",
                 "pairs_per_pose": pairs, "flop_per_pair": FLOP_PER_PAIR,
@@ -315,6 +317,26 @@ def extra_ops(vt, peaks, args):
     gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
     res["smooth_sigma2"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8,
                             "note": "3 separable passes move 24 B/voxel"}
+    def resample_leg(op):
+        vt.profile_reset(); vt.profile_enable(True)
+        reps = 3
+        for _ in range(reps):
+            M = A.clone()
+            getattr(M, op)()
+            del M
+        ms, cnt = vt.profile_get("resample")
+        vt.profile_enable(False)
+        return ms / reps
+    getattr(A.clone(), "downsample")()
+    ms = resample_leg("downsample")
+    gbs = 4.5 * g.n / (ms * 1e-3) / 1e9
+    res["downsample"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_input_voxel": 4.5}
+    if n <= 512:
+        getattr(A.clone(), "supersample")()
+        ms = resample_leg("supersample")
+        gbs = 36.0 * g.n / (ms * 1e-3) / 1e9
+        res["supersample"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_input_voxel": 36,
+                              "out": [2 * n - 1] * 3}
     del A, B, C
     # cfg1: sim + cc, 10k atoms, res 5, 1 A spacing
     from voltool_b200.synth import make_structure

@@ -109,43 +109,76 @@ __device__ __forceinline__ float xline(const float *__restrict__ row, int ox, in
 }
 
 // pass 1: every EVEN output plane (Z = 2gz): x then y interpolation (:783-875).  The y stencil is
-// evaluated on x-interpolated rows, exactly as the reference's in-place sweeps leave them.
+// evaluated on x-interpolated rows, exactly as the reference's in-place sweeps leave them.  A CTA
+// owns kYB source rows of one plane: it stages the x-interpolated lines of those rows (+1 below,
+// +2 above, clamped) in shared memory once, then every output row is either a copy (even Y) or one
+// cubic over four staged lines (odd Y).
+constexpr int kYB = 8;
+
 __global__ void __launch_bounds__(kThreads) supersample_xy_kernel(const float *__restrict__ src, int ox, int oy,
                                                                   int oz, float *__restrict__ dst, int nx, int ny) {
-  const long rows = (long)ny * oz;
+  extern __shared__ float lines[];  // (kYB + 3) x nx
+  const int yblocks = (oy + kYB - 1) / kYB;
+  const long work = (long)yblocks * oz;
   const long oxy = (long)ox * oy, nxy = (long)nx * ny;
-  for (long r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int Y = (int)(r % ny), gz = (int)(r / ny);
+  for (long w = blockIdx.x; w < work; w += gridDim.x) {
+    const int yb = (int)(w % yblocks), gz = (int)(w / yblocks);
+    const int g0 = yb * kYB;
     const float *plane = src + gz * oxy;
-    float *out = dst + 2L * gz * nxy + (long)Y * nx;
-    const int g = Y >> 1;
-    if ((Y & 1) == 0) {
+    // staged line l <-> source row clamp(g0 - 1 + l)
+    for (int l = 0; l < kYB + 3; ++l) {
+      int g = g0 - 1 + l;
+      g = g < 0 ? 0 : (g > oy - 1 ? oy - 1 : g);
       const float *row = plane + (long)g * ox;
-      for (int X = threadIdx.x; X < nx; X += blockDim.x) out[X] = xline(row, ox, X);
-    } else {
-      const int gm = g > 0 ? g - 1 : 0;
-      const int gp = g + 2 < oy ? g + 2 : oy - 1;
-      const float *r0 = plane + (long)gm * ox, *r1 = plane + (long)g * ox;
-      const float *r2 = plane + (long)(g + 1) * ox, *r3 = plane + (long)gp * ox;
-      for (int X = threadIdx.x; X < nx; X += blockDim.x)
-        out[X] = cubic_half(xline(r0, ox, X), xline(r1, ox, X), xline(r2, ox, X), xline(r3, ox, X));
+      for (int X = threadIdx.x; X < nx; X += blockDim.x) lines[l * nx + X] = xline(row, ox, X);
     }
+    __syncthreads();
+    float *out = dst + 2L * gz * nxy;
+    for (int r = 0; r < 2 * kYB; ++r) {
+      const int Y = 2 * g0 + r;
+      if (Y >= ny) break;
+      const int g = Y >> 1;  // source row below / at this output row; its line is l = g - g0 + 1
+      float *o = out + (long)Y * nx;
+      if ((Y & 1) == 0) {
+        const float *ln = lines + (g - g0 + 1) * nx;
+        for (int X = threadIdx.x; X < nx; X += blockDim.x) o[X] = ln[X];
+      } else {
+        // rows g-1, g, g+1, g+2 with the end rows replicated (:841-875); the staged lines are already
+        // clamped at the volume edges, so the neighbours are simply l-1 .. l+2
+        const int l = g - g0 + 1;
+        const float *l0 = lines + (l - 1) * nx, *l1 = lines + l * nx, *l2 = lines + (l + 1) * nx, *l3 = lines + (l + 2) * nx;
+        for (int X = threadIdx.x; X < nx; X += blockDim.x) o[X] = cubic_half(l0[X], l1[X], l2[X], l3[X]);
+      }
+    }
+    __syncthreads();
   }
 }
 
-// pass 2: every ODD output plane from the four surrounding even planes (:878-913)
+// pass 2: every ODD output plane from the four surrounding even planes (:878-913).  A thread owns
+// one (X,Y) column of a z chunk and slides a 4-plane window along z, so each even plane is read
+// once per chunk.
+constexpr int kZB = 64;
+
 __global__ void __launch_bounds__(kThreads) supersample_z_kernel(float *__restrict__ dst, int nx, int ny, int oz) {
   const long nxy = (long)nx * ny;
-  const long total = nxy * (oz - 1);
+  const int zchunks = (oz - 1 + kZB - 1) / kZB;
+  const long work = nxy * zchunks;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int g = (int)(i / nxy);
-    const long r = i - (long)g * nxy;
-    const int gm = g > 0 ? g - 1 : 0;
-    const int gp = g + 2 < oz ? g + 2 : oz - 1;
-    const float v = cubic_half(dst[r + 2L * gm * nxy], dst[r + 2L * g * nxy], dst[r + 2L * (g + 1) * nxy],
-                               dst[r + 2L * gp * nxy]);
-    dst[r + (2L * g + 1) * nxy] = v;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < work; i += stride) {
+    const int zc = (int)(i / nxy);
+    const long r = i - (long)zc * nxy;
+    const int gbeg = zc * kZB, gend = min(oz - 1, gbeg + kZB);
+    float *col = dst + r;
+    // window over source planes g-1, g, g+1, g+2 (clamped)
+    float vm = col[2L * (gbeg > 0 ? gbeg - 1 : 0) * nxy];
+    float v0 = col[2L * gbeg * nxy];
+    float v1 = col[2L * (gbeg + 1) * nxy];
+    for (int g = gbeg; g < gend; ++g) {
+      const int gp = g + 2 < oz ? g + 2 : oz - 1;
+      const float v2 = gp == g + 1 ? v1 : col[2L * gp * nxy];
+      col[(2L * g + 1) * nxy] = cubic_half(vm, v0, v1, v2);
+      vm = v0; v0 = v1; v1 = v2;
+    }
   }
 }
 
@@ -156,7 +189,15 @@ int k_supersample(const float *src, int ox, int oy, int oz, float *dst) {
   long rows = (long)ny * oz;
   int grid = (int)(rows < (long)ctx().sm_count * 16 ? rows : (long)ctx().sm_count * 16);
   prof_begin(PK_RESAMPLE);
-  supersample_xy_kernel<<<grid, kThreads, 0, ctx().stream>>>(src, ox, oy, oz, dst, nx, ny);
+  const size_t smem = sizeof(float) * (size_t)(kYB + 3) * nx;
+  if (smem > 200 * 1024) { set_error("vt_supersample: rows too long (%d)", ox); return 1; }
+  if (smem > 48 * 1024)
+    VT_CUDA(cudaFuncSetAttribute(supersample_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    const long work = (long)((oy + kYB - 1) / kYB) * oz;
+    grid = (int)(work < (long)ctx().sm_count * 8 ? work : (long)ctx().sm_count * 8);
+  }
+  supersample_xy_kernel<<<grid, kThreads, smem, ctx().stream>>>(src, ox, oy, oz, dst, nx, ny);
   VT_LAUNCHED();
   supersample_z_kernel<<<ctx().sm_count * 8, kThreads, 0, ctx().stream>>>(dst, nx, ny, oz);
   prof_end(PK_RESAMPLE);
