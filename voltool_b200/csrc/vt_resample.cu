@@ -130,7 +130,17 @@ __global__ void __launch_bounds__(kThreads) supersample_xy_kernel(const float *_
       int g = g0 - 1 + l;
       g = g < 0 ? 0 : (g > oy - 1 ? oy - 1 : g);
       const float *row = plane + (long)g * ox;
-      for (int X = threadIdx.x; X < nx; X += blockDim.x) lines[l * nx + X] = xline(row, ox, X);
+      // thread t makes the pair (2t, 2t+1): no even/odd divergence, the four source values are shared
+      float *ln = lines + l * nx;
+      for (int t = threadIdx.x; t < ox; t += blockDim.x) {
+        const float v1 = __ldg(row + t);
+        ln[2 * t] = v1;
+        if (t + 1 < ox) {
+          const float v0 = __ldg(row + (t > 0 ? t - 1 : 0)), v2 = __ldg(row + t + 1);
+          const float v3 = __ldg(row + (t + 2 < ox ? t + 2 : ox - 1));
+          ln[2 * t + 1] = cubic_half(v0, v1, v2, v3);
+        }
+      }
     }
     __syncthreads();
     float *out = dst + 2L * gz * nxy;
@@ -173,7 +183,21 @@ __global__ void __launch_bounds__(kThreads) supersample_z_kernel(float *__restri
     float vm = col[2L * (gbeg > 0 ? gbeg - 1 : 0) * nxy];
     float v0 = col[2L * gbeg * nxy];
     float v1 = col[2L * (gbeg + 1) * nxy];
-    for (int g = gbeg; g < gend; ++g) {
+    int g = gbeg;
+    for (; g + 4 <= gend; g += 4) {  // four independent loads ahead of the dependent window shifts
+      float w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int gp = g + q + 2 < oz ? g + q + 2 : oz - 1;
+        w[q] = col[2L * gp * nxy];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        col[(2L * (g + q) + 1) * nxy] = cubic_half(vm, v0, v1, w[q]);
+        vm = v0; v0 = v1; v1 = w[q];
+      }
+    }
+    for (; g < gend; ++g) {
       const int gp = g + 2 < oz ? g + 2 : oz - 1;
       const float v2 = gp == g + 1 ? v1 : col[2L * gp * nxy];
       col[(2L * g + 1) * nxy] = cubic_half(vm, v0, v1, v2);
