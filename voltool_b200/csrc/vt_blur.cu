@@ -7,6 +7,8 @@
 // Pass structure: the x pass stages each row segment (+halo) in shared memory; the y and z
 // passes march a register window along the filtered axis so each input element is read from
 // L2/HBM once per pass.
+#include <climits>
+#include <algorithm>
 #include <cstdlib>
 
 #include "vt_device.cuh"
@@ -209,6 +211,153 @@ __global__ void __launch_bounds__(256) blur_axis_fixed_kernel(const float *__res
   }
 }
 
+// x and y passes of one plane tile in a single kernel: a CTA x-blurs the kXT x (kYT + 2R) rows the tile's
+// y pass needs into shared memory (aligned float4 windows straight from global memory, as
+// blur_x_direct_kernel), then each thread y-blurs 8 outputs of one column from a register window.
+// The intermediate never leaves the SM, so the blur costs two passes over HBM instead of three; the
+// arithmetic per output is the reference's (VolumetricData.C:946-1000: taps in order, x then y).
+constexpr int kXT = 32, kYT = 64;
+
+template <int R>
+__global__ void __launch_bounds__(256) blur_xy_kernel(const float *__restrict__ in, float *__restrict__ out, int nx,
+                                                      int ny, int nz, int xt, int yt, int zchunk) {
+  constexpr int HR = kYT + 2 * R;
+  constexpr int OFF = (4 - (R & 3)) & 3;  // left slack so that windows start 16-byte aligned
+  constexpr int NQ = (OFF + 4 + 2 * R + 3) / 4;
+  constexpr int NSEG = HR * (kXT / 4);
+  constexpr int ITER = (NSEG + 255) / 256;
+  __shared__ __align__(16) float sxbuf[2][HR * kXT];
+  const int tid = threadIdx.x;
+  const long w = blockIdx.x;
+  const int tx0 = (int)(w % xt) * kXT, ty0 = (int)((w / xt) % yt) * kYT, z0 = (int)(w / ((long)xt * yt)) * zchunk;
+  const int z1 = min(nz, z0 + zchunk);
+  const long nxy = (long)nx * ny;
+  // z-invariant description of this thread's x segments
+  int soff[ITER];    // voxel offset of the window start inside a plane (row * nx + xs); xs may be < 0
+  int sxs[ITER];     // xs, or INT_MIN when the segment does not exist
+  int sdst[ITER];    // shared-memory float index of the 4 outputs
+  bool edge[ITER];   // window crosses a row end
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int sg = tid + 256 * it;
+    const int row = sg / (kXT / 4), sx0 = (sg - row * (kXT / 4)) * 4;
+    int y = ty0 - R + row;
+    y = y < 0 ? 0 : (y > ny - 1 ? ny - 1 : y);
+    const int xs = tx0 + sx0 - R - OFF;
+    sxs[it] = sg < NSEG ? xs : INT_MIN;
+    soff[it] = y * nx + xs;
+    sdst[it] = row * kXT + sx0;
+    edge[it] = xs < 0 || xs + 4 * NQ > nx;
+  }
+  const int x = tid & 31, yb = (tid >> 5) * 8;
+  const int gx = tx0 + x;
+  const bool colok = gx < nx;
+  const int rows_ok = min(8, ny - (ty0 + yb));   // outputs of this thread that are inside the map
+  const long ooff = (long)(ty0 + yb) * nx + gx;
+  int buf = 0;
+  for (int z = z0; z < z1; ++z, buf ^= 1) {
+    const float *plane = in + (long)z * nxy;
+    float *sx = sxbuf[buf];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      if (sxs[it] == INT_MIN) continue;
+      float v[4 * NQ];
+      if (!edge[it]) {
+        const float4 *p = reinterpret_cast<const float4 *>(plane + soff[it]);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float4 f = __ldg(p + q);
+          v[4 * q + 0] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+      } else {
+        // xs and nx are multiples of 4, so an aligned quad is wholly inside the row or wholly
+        // outside: outside quads are a splat of the row's first / last voxel (clamp-to-edge)
+        const float *rowp = plane + (soff[it] - sxs[it]);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int j = sxs[it] + 4 * q;
+          const int jc = j < 0 ? 0 : (j > nx - 4 ? nx - 4 : j);
+          float4 f = __ldg(reinterpret_cast<const float4 *>(rowp + jc));
+          if (j < 0) f = make_float4(f.x, f.x, f.x, f.x);
+          if (j > nx - 4) f = make_float4(f.w, f.w, f.w, f.w);
+          v[4 * q + 0] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+      }
+      float acc[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        float a = 0.0f;
+#pragma unroll
+        for (int k = 0; k <= 2 * R; ++k) a = __fmaf_rn(c_taps[k], v[OFF + s + k], a);
+        acc[s] = a;
+      }
+      *reinterpret_cast<float4 *>(sx + sdst[it]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+    __syncthreads();   // one barrier per plane: the other buffer is only rewritten after the next one
+    float v[8 + 2 * R];
+#pragma unroll
+    for (int t = 0; t < 8 + 2 * R; ++t) v[t] = sx[(yb + t) * kXT + x];
+    float *dst = out + (long)z * nxy + ooff;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      float a = 0.0f;
+#pragma unroll
+      for (int k = 0; k <= 2 * R; ++k) a = __fmaf_rn(c_taps[k], v[s + k], a);
+      if (colok && s < rows_ok) dst[s * nx] = a;
+    }
+  }
+}
+
+// z pass, four consecutive x per thread: SEG output planes from a sliding window of SEG + 2R input
+// quads (taps in reference order per output).  blockIdx.y selects the plane segment.
+template <int R, int SEG>
+__global__ void __launch_bounds__(256) blur_z4_kernel(const float *__restrict__ in, float *__restrict__ out, long quads,
+                                                      int nz) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= quads) return;
+  const int a0 = blockIdx.y * SEG;
+  const float4 *src = reinterpret_cast<const float4 *>(in) + q;
+  float4 *dst = reinterpret_cast<float4 *>(out) + q;
+  float4 acc[SEG];
+#pragma unroll
+  for (int s = 0; s < SEG; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < SEG + 2 * R; ++t) {
+    int j = a0 - R + t;
+    j = j < 0 ? 0 : (j > nz - 1 ? nz - 1 : j);
+    const float4 v = __ldg(src + (long)j * quads);
+#pragma unroll
+    for (int s = 0; s < SEG; ++s)
+      if (t - s >= 0 && t - s <= 2 * R) {
+        const float c = c_taps[t - s];
+        acc[s].x = __fmaf_rn(c, v.x, acc[s].x); acc[s].y = __fmaf_rn(c, v.y, acc[s].y);
+        acc[s].z = __fmaf_rn(c, v.z, acc[s].z); acc[s].w = __fmaf_rn(c, v.w, acc[s].w);
+      }
+  }
+#pragma unroll
+  for (int s = 0; s < SEG; ++s)
+    if (a0 + s < nz) dst[(long)(a0 + s) * quads] = acc[s];
+}
+
+// x+y fused pass into tmp, then the z pass into dst
+template <int R>
+static int blur_two_pass(const float *src, float *dst, float *tmp, int nx, int ny, int nz) {
+  Ctx &c = ctx();
+  const int xt = (nx + kXT - 1) / kXT, yt = (ny + kYT - 1) / kYT;
+  const int zchunk = 16;
+  const long work = (long)xt * yt * ((nz + zchunk - 1) / zchunk);
+  // unaligned rows (or planes beyond int offsets): three-pass path
+  if (work > 0x7fffffffL || (nx & 3) != 0 || nx < 4 || (long)nx * ny > 0x7fffffffL) return 1;
+  blur_xy_kernel<R><<<(unsigned int)work, 256, 0, c.stream>>>(src, tmp, nx, ny, nz, xt, yt, zchunk);
+  VT_LAUNCHED();
+  constexpr int SEG = 16;
+  const long quads = (long)nx * ny / 4;
+  const dim3 gz((unsigned int)((quads + 255) / 256), (unsigned int)((nz + SEG - 1) / SEG));
+  blur_z4_kernel<R, SEG><<<gz, 256, 0, c.stream>>>(tmp, dst, quads, nz);
+  VT_LAUNCHED();
+  return 0;
+}
+
 template <int R>
 static int blur_fixed(const float *src, float *dst, float *tmp, int nx, int ny, int nz) {
   Ctx &c = ctx();
@@ -250,6 +399,22 @@ int k_blur(const float *src, float *dst, float *tmp, int nx, int ny, int nz, con
   if (grid < 1) grid = 1;
   // x: src -> dst ; y: dst -> tmp ; z: tmp -> dst
   prof_begin(PK_BLUR);
+  if (!getenv("VOLTOOL_BLUR_GENERIC") && !getenv("VOLTOOL_BLUR_SEPARATE")) {
+    int rc = 1;
+    switch (R) {
+      case 1: rc = blur_two_pass<1>(src, dst, tmp, nx, ny, nz); break;
+      case 2: rc = blur_two_pass<2>(src, dst, tmp, nx, ny, nz); break;
+      case 3: rc = blur_two_pass<3>(src, dst, tmp, nx, ny, nz); break;
+      case 4: rc = blur_two_pass<4>(src, dst, tmp, nx, ny, nz); break;
+      case 5: rc = blur_two_pass<5>(src, dst, tmp, nx, ny, nz); break;
+      case 6: rc = blur_two_pass<6>(src, dst, tmp, nx, ny, nz); break;
+      case 7: rc = blur_two_pass<7>(src, dst, tmp, nx, ny, nz); break;
+      case 8: rc = blur_two_pass<8>(src, dst, tmp, nx, ny, nz); break;
+      default: break;
+    }
+    if (rc == 0) { prof_end(PK_BLUR); return 0; }
+    if (rc > 1) return rc;
+  }
   if (!getenv("VOLTOOL_BLUR_GENERIC")) {
     int rc = 1;
     switch (R) {
