@@ -104,6 +104,42 @@ def test_cc_staged_ring_path(oracle, monkeypatch):
             assert abs(ref - want) <= 1e-9 and abs(got - want) <= 1e-7, (got, ref, want)
 
 
+def test_cc_identity_stream_path(oracle, monkeypatch):
+    """maps on one exactly representable lattice (whole-voxel shifts allowed) are streamed once without
+    interpolation; a NaN/inf/huge voxel anywhere sends the call back to the interpolating path"""
+    r = np.random.default_rng(12)
+    cases = [(OGrid.make((0, 0, 0), (64, 60, 56), 1.0), OGrid.make((0, 0, 0), (64, 60, 56), 1.0)),        # identical
+             (OGrid.make((0, 0, 0), (40, 36, 32), 1.0), OGrid.make((-4, -8, -2), (64, 60, 56), 1.0)),     # aligned sub-box
+             (OGrid.make((0, 0, 0), (40, 36, 32), 0.5), OGrid.make((-1.5, -4, -1), (64, 60, 56), 0.5)),   # x shift 3: scalar loads
+             (OGrid.make((2, 2, 2), (37, 21, 19), 2.0), OGrid.make((2, 2, 2), (37, 21, 19), 2.0))]        # odd sizes
+    for A, B in cases:
+        a, b = r.random(A.n, dtype=np.float32), r.random(B.n, dtype=np.float32)
+        for thr in (-FLT_MAX, 0.4):
+            want, nw, sw = oracle.cc(A, a, B, b, thr, full=True)
+            monkeypatch.setenv("VOLTOOL_CC_IDENTITY", "1")
+            got, ng, sg = vt.cc_threaded(vt.VolMap(G(A), a), vt.VolMap(G(B), b), thr, full=True)
+            monkeypatch.setenv("VOLTOOL_CC_IDENTITY", "0")
+            ref, nr, _ = vt.cc_threaded(vt.VolMap(G(A), a), vt.VolMap(G(B), b), thr, full=True)
+            monkeypatch.delenv("VOLTOOL_CC_IDENTITY")
+            assert ng == nw == nr
+            assert abs(ref - want) <= 1e-9 and abs(got - want) <= 1e-7, (got, ref, want)
+            assert np.allclose(sg, sw, rtol=1e-6)
+        # values that break "sample == voxel": the answer must still be the oracle's
+        for poison in (np.nan, np.inf, -3.0e38):
+            for which in (0, 1):
+                a2, b2 = a.copy(), b.copy()
+                (a2 if which == 0 else b2)[::997] = poison
+                want, nw, _ = oracle.cc(A, a2, B, b2, 0.2, full=True)
+                monkeypatch.setenv("VOLTOOL_CC_IDENTITY", "1")
+                got, ng, _ = vt.cc_threaded(vt.VolMap(G(A), a2), vt.VolMap(G(B), b2), 0.2, full=True)
+                monkeypatch.delenv("VOLTOOL_CC_IDENTITY")
+                assert ng == nw
+                if np.isnan(want):
+                    assert np.isnan(got)
+                else:
+                    assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (poison, which, got, want)
+
+
 def test_cc_known_answers():
     g = vt.Grid.make((0, 0, 0), (64, 60, 56), 1.0)
     a = rng_map(5, g.n)

@@ -14,6 +14,8 @@
 //             the bilinear value of the shared plane between consecutive z steps when the index
 //             advances by one.
 #include <cmath>
+#include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "vt_device.cuh"
@@ -126,6 +128,99 @@ static int upload_tables(const DevCoord &C, const DevMap &A, const DevMap &B, Se
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ identity CC
+// When every table entry of both maps is "inside, fraction exactly 0, index = g + const" (two maps
+// on one lattice with exactly representable spacing, or one a whole-voxel-shifted sub-box of the
+// other) each trilinear sample is a0 + 0*(a1-a0) + ... = the voxel itself, provided no neighbour is
+// NaN/inf and no difference overflows (0*inf would poison the sample, VolumetricData.C:273-287).
+// The kernel streams both maps once with 16-byte loads and raises `bad` if it meets a value that
+// could break that (non-finite or |v| >= 2^126); the host then discards the result and takes the
+// interpolating path.  A -0 voxel may sample as +0 in the reference: irrelevant to the sums.
+struct IdentArgs {
+  const float *a, *b;           // first voxel of the common box in each map
+  long a_row, a_plane, b_row, b_plane;
+  int nx, ny, nz;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) cc_identity_kernel(IdentArgs g, float thr_f, double *partials,
+                                                               unsigned int *ticket, double *out, int *bad_out) {
+  __shared__ double sm[6 * 32];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  long long nvox = 0;
+  bool bad = false;
+  constexpr int W = VEC ? 4 : 1;            // voxels per lane per load
+  constexpr int U = 4;                      // loads in flight per lane and map
+  const unsigned int rows = (unsigned int)g.ny * (unsigned int)g.nz;
+  const int lane = threadIdx.x & 31;
+  const unsigned int wstride = gridDim.x * (kThreads / 32);
+  // a warp owns whole rows: one 32-bit division per row, 2 x U independent 16-byte loads per trip
+  for (unsigned int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    const unsigned int z = row / (unsigned int)g.ny, y = row - z * (unsigned int)g.ny;
+    const float *pa = g.a + z * g.a_plane + y * g.a_row;
+    const float *pb = g.b + z * g.b_plane + y * g.b_row;
+    for (int x0 = lane * W; x0 < g.nx; x0 += 32 * W * U) {
+      float va[U][W], vb[U][W];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int x = x0 + u * 32 * W;
+        const bool in = x < g.nx;
+        if (VEC) {
+          float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
+          if (in) { fa = __ldcs(reinterpret_cast<const float4 *>(pa + x)); fb = __ldcs(reinterpret_cast<const float4 *>(pb + x)); }
+          va[u][0] = fa.x; va[u][W > 1 ? 1 : 0] = fa.y; va[u][W > 1 ? 2 : 0] = fa.z; va[u][W > 1 ? 3 : 0] = fa.w;
+          vb[u][0] = fb.x; vb[u][W > 1 ? 1 : 0] = fb.y; vb[u][W > 1 ? 2 : 0] = fb.z; vb[u][W > 1 ? 3 : 0] = fb.w;
+        } else {
+          va[u][0] = in ? __ldcs(pa + x) : 0.f;
+          vb[u][0] = in ? __ldcs(pb + x) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool in = x0 + u * 32 * W < g.nx;
+        float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          bad = bad || !(fabsf(va[u][k]) < 8.0e37f) || !(fabsf(vb[u][k]) < 8.0e37f);
+          const bool take = in && va[u][k] >= thr_f;             // MDFF.C:73-77 (NaNs raise `bad`)
+          const float a = take ? va[u][k] : 0.f, b = take ? vb[u][k] : 0.f;
+          fA += a; fB += b;
+          fAA += a * a; fBB += b * b; fAB += a * b;              // float products, as MDFF.C:81-83
+          cnt += take ? 1 : 0;
+        }
+        acc[0] += (double)fA; acc[1] += (double)fB; acc[2] += (double)fAA; acc[3] += (double)fBB;
+        acc[4] += (double)fAB;
+        nvox += cnt;
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(bad_out, 1);
+  acc[5] = (double)nvox;
+  block_sum<6>(acc, sm);
+  grid_finish<6>(acc, partials, ticket, out, sm);
+}
+
+// Host: do the six tables describe whole-voxel identity sampling?  shift[m][axis] = index offset.
+static bool identity_tables(const std::vector<AxisEntry> &tab, const int off[6], const int nout[3], const DevMap &A,
+                            const DevMap &B, int shift[2][3]) {
+  const DevMap *maps[2] = {&A, &B};
+  for (int m = 0; m < 2; ++m) {
+    const int nsrc[3] = {maps[m]->nx, maps[m]->ny, maps[m]->nz};
+    for (int ax = 0; ax < 3; ++ax) {
+      const AxisEntry *t = &tab[off[3 * m + ax]];
+      const int c0 = t[0].i0;
+      for (int gi = 0; gi < nout[ax]; ++gi) {
+        const AxisEntry &e = t[gi];
+        if (!e.inside || e.f != 0.0f || e.i0 != c0 + gi) return false;
+        if (e.i1 != e.i0 + 1 && !(e.i1 == e.i0 && e.i0 == nsrc[ax] - 1)) return false;
+      }
+      shift[m][ax] = c0;
+    }
+  }
+  return true;
+}
+
 constexpr int kZChunk = 32;  // output z steps per warp work item
 
 __global__ void __launch_bounds__(kThreads, 2) cc_sep_kernel(DevMap A, DevMap B, int nx, int ny, int nz,
@@ -185,6 +280,43 @@ int k_cc(const vt_map *A, const vt_map *B, double thr, double sums[5], long *n) 
     const char *force = getenv("VOLTOOL_CC_STAGED");
     const bool want_staged = force ? atoi(force) != 0 : vox >= (8L << 20);
     int st = 1;
+    // whole-voxel identity sampling: one streaming pass, unless the data turn out to hold a value
+    // that makes "sample == voxel" unsafe
+    int shift[2][3];
+    const int nout[3] = {og.xsize, og.ysize, og.zsize};
+    // (large maps only, like the ring kernel: its sums go through float per 4 voxels)
+    const char *fid = getenv("VOLTOOL_CC_IDENTITY");
+    const bool want_ident = fid ? atoi(fid) != 0 : vox >= (8L << 20);
+    if (want_ident && (long)og.ysize * og.zsize < (1L << 31) &&
+        identity_tables(T.host, T.off, nout, dA, dB, shift)) {
+      IdentArgs ia;
+      ia.a_row = dA.nx; ia.a_plane = (long)dA.nx * dA.ny;
+      ia.b_row = dB.nx; ia.b_plane = (long)dB.nx * dB.ny;
+      ia.a = dA.d + shift[0][2] * ia.a_plane + shift[0][1] * ia.a_row + shift[0][0];
+      ia.b = dB.d + shift[1][2] * ia.b_plane + shift[1][1] * ia.b_row + shift[1][0];
+      ia.nx = og.xsize; ia.ny = og.ysize; ia.nz = og.zsize;
+      const bool vec = (og.xsize % 4 == 0) && (dA.nx % 4 == 0) && (dB.nx % 4 == 0) &&
+                       ((uintptr_t)ia.a % 16 == 0) && ((uintptr_t)ia.b % 16 == 0);
+      int *d_bad = reinterpret_cast<int *>(dout + 6);
+      VT_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c.stream));
+      const long wblocks = ((long)og.ysize * og.zsize + kThreads / 32 - 1) / (kThreads / 32);
+      const int grid = (int)(wblocks < (long)c.sm_count * 8 ? wblocks : (long)c.sm_count * 8);
+      prof_begin(PK_CC);
+      if (vec) cc_identity_kernel<true><<<grid, kThreads, 0, c.stream>>>(ia, threshold_as_float(thr), partials, c.d_ticket, dout, d_bad);
+      else cc_identity_kernel<false><<<grid, kThreads, 0, c.stream>>>(ia, threshold_as_float(thr), partials, c.d_ticket, dout, d_bad);
+      prof_end(PK_CC);
+      VT_LAUNCHED();
+      VT_CUDA(cudaMemcpyAsync(c.h_pinned, dout, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      VT_CUDA(cudaStreamSynchronize(c.stream));
+      int bad;
+      memcpy(&bad, &c.h_pinned[6], sizeof(int));
+      if (!bad) {
+        dev_free(T.d);
+        for (int k = 0; k < 5; ++k) sums[k] = c.h_pinned[k];
+        *n = (long)c.h_pinned[5];
+        return 0;
+      }
+    }
     if (want_staged)
       st = k_cc_staged(dA, dB, og.xsize, og.ysize, og.zsize, T.host, T.off, T.d, threshold_as_float(thr), partials,
                        c.d_ticket, dout);

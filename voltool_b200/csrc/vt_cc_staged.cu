@@ -129,9 +129,9 @@ __device__ __forceinline__ void consumer_init(Consumer<Y> &c, const AxisEntry &e
 
 // bilinear values of the staged plane for this thread's rows: a0 + xf*(a1-a0) per source row,
 // then the y lerp (voxel_value_interpolate, VolumetricData.C:273-287)
-template <int Y>
+template <int Y, bool KNOWN_UNIT = false>
 __device__ __forceinline__ void consumer_plane(const Consumer<Y> &c, const float *__restrict__ P, float (&out)[Y]) {
-  if (c.unit) {
+  if (KNOWN_UNIT || c.unit) {
     const float *__restrict__ q = P + c.base;
     const float *__restrict__ q1 = P + c.base1;
     float xl[Y + 1];
@@ -162,13 +162,13 @@ __device__ __forceinline__ void consumer_plane(const Consumer<Y> &c, const float
 }
 
 // take the next plane of this map's ring (planes arrive strictly in order)
-template <int Y>
+template <int Y, bool KNOWN_UNIT = false>
 __device__ __forceinline__ void consumer_take(const Consumer<Y> &c, const float *__restrict__ ring,
                                               unsigned long long *full, unsigned long long *empty, unsigned int &cnt,
                                               int plane_floats, float (&out)[Y]) {
   const unsigned int slot = cnt % S, par = (cnt / S) & 1u;
   mbar_wait(&full[slot], par);
-  consumer_plane<Y>(c, ring + (size_t)slot * plane_floats, out);
+  consumer_plane<Y, KNOWN_UNIT>(c, ring + (size_t)slot * plane_floats, out);
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);
   ++cnt;
@@ -211,6 +211,17 @@ __device__ __forceinline__ void producer_run(const float *__restrict__ src, int 
     for (int r = lane; r < b.nrows; r += 32) bulk_g2s(dst + r * XS, g + (size_t)r * snx, wbytes, &full[slot]);
     ++cnt;
   }
+}
+
+// every step of [za, zb) uses source planes (k, k+1) with k advancing by exactly one (warp-wide check)
+__device__ __forceinline__ bool chunk_regular(const AxisEntry *__restrict__ t, int za, int zb) {
+  bool ok = true;
+  for (int g = za + (int)(threadIdx.x & 31); g < zb; g += 32) {
+    const AxisEntry e = t[g];
+    ok = ok && (e.i1 == e.i0 + 1);
+    if (g + 1 < zb) ok = ok && (t[g + 1].i0 == e.i0 + 1);
+  }
+  return __all_sync(0xffffffffu, ok);
 }
 
 // MODE 0: cross correlation sums.  MODE 1..5: two-map op written to outp (Voltool.C:249-377):
@@ -283,51 +294,83 @@ __global__ void __launch_bounds__(kThreadsStaged, (Y > 4 ? 1 : 2))
         inB[r] = bx.inside && tBy[gyc].inside;
         ok[r] = gx < nx && gy < ny;
       }
-      for (int gz = za; gz < zb; ++gz) {
-        const AxisEntry az = tAz[gz], bz = tBz[gz];
-        float va[Y], vb[Y];
-        consumer_sample<Y>(ca, az, ringA, fullA, emptyA, cntA, plane_floats, va);
-        consumer_sample<Y>(cb, bz, ringB, fullB, emptyB, cntB, plane_floats, vb);
-        if (MODE == 0) {
-          float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;
-          int cnt = 0;
-#pragma unroll
-          for (int r = 0; r < Y; ++r) {
-            const bool take = ok[r] && inA[r] && inB[r] && (va[r] >= thr_f) && (vb[r] == vb[r]);  // MDFF.C:73-77
-            const float a = take ? va[r] : 0.f, b = take ? vb[r] : 0.f;
-            fA += a; fB += b;
-            fAA += a * a; fBB += b * b; fAB += a * b;
-            cnt += take ? 1 : 0;
-          }
-          acc[0] += (double)fA; acc[1] += (double)fB; acc[2] += (double)fAA; acc[3] += (double)fBB;
-          acc[4] += (double)fAB;
-          nvox += cnt;
-        } else {
-          constexpr bool SAFE = (MODE != 3 && MODE != 4);  // add/sub/avg read 0 outside, multiply reads NaN
-#pragma unroll
-          for (int r = 0; r < Y; ++r) {
-            if (!ok[r]) continue;
-            const int gy = gy0 + r;
-            float a = inA[r] ? va[r] : (SAFE ? 0.0f : quiet_nan());
-            float b = inB[r] ? vb[r] : (SAFE ? 0.0f : quiet_nan());
-            if (a != a || b != b) {
-              // a NaN is involved: redo this voxel with the literal per-voxel arithmetic so that the
-              // x86 payload rules of the reference are reproduced
-              float x, y, z;
-              voxel_coord(ba.gC, gx, gy, gz, x, y, z);
-              a = sample_interp<SAFE>(ba.gA, x, y, z);
-              b = sample_interp<SAFE>(ba.gB, x, y, z);
+      // one output plane of this warp's rows: the CC sums or the two-map op
+      auto emit = [&](int gz, const float (&va)[Y], const float (&vb)[Y]) {
+          if (MODE == 0) {
+            float fA = 0.f, fB = 0.f, fAA = 0.f, fBB = 0.f, fAB = 0.f;
+            int cnt = 0;
+  #pragma unroll
+            for (int r = 0; r < Y; ++r) {
+              const bool take = ok[r] && inA[r] && inB[r] && (va[r] >= thr_f) && (vb[r] == vb[r]);  // MDFF.C:73-77
+              const float a = take ? va[r] : 0.f, b = take ? vb[r] : 0.f;
+              fA += a; fB += b;
+              fAA += a * a; fBB += b * b; fAB += a * b;
+              cnt += take ? 1 : 0;
             }
-            float v;
-            if (MODE == 1) v = nan_like_x86(a + b, a, b);
-            else if (MODE == 2) v = nan_like_x86(a - b, a, b);
-            else if (MODE == 3) v = nan_like_x86(a * b, a, b);
-            else if (MODE == 4) {
-              const bool na = is_nan_bits(a), nb = is_nan_bits(b);
-              v = (!na && !nb) ? nan_like_x86(a * b, a, b) : (!na ? a : (!nb ? b : 0.0f));
-            } else v = nan_like_x86((float)((double)(a + b) * 0.5), a, b);
-            ba.outp[((size_t)gz * ny + gy) * nx + gx] = v;
+            acc[0] += (double)fA; acc[1] += (double)fB; acc[2] += (double)fAA; acc[3] += (double)fBB;
+            acc[4] += (double)fAB;
+            nvox += cnt;
+          } else {
+            constexpr bool SAFE = (MODE != 3 && MODE != 4);  // add/sub/avg read 0 outside, multiply reads NaN
+  #pragma unroll
+            for (int r = 0; r < Y; ++r) {
+              if (!ok[r]) continue;
+              const int gy = gy0 + r;
+              float a = inA[r] ? va[r] : (SAFE ? 0.0f : quiet_nan());
+              float b = inB[r] ? vb[r] : (SAFE ? 0.0f : quiet_nan());
+              if (a != a || b != b) {
+                // a NaN is involved: redo this voxel with the literal per-voxel arithmetic so that the
+                // x86 payload rules of the reference are reproduced
+                float x, y, z;
+                voxel_coord(ba.gC, gx, gy, gz, x, y, z);
+                a = sample_interp<SAFE>(ba.gA, x, y, z);
+                b = sample_interp<SAFE>(ba.gB, x, y, z);
+              }
+              float v;
+              if (MODE == 1) v = nan_like_x86(a + b, a, b);
+              else if (MODE == 2) v = nan_like_x86(a - b, a, b);
+              else if (MODE == 3) v = nan_like_x86(a * b, a, b);
+              else if (MODE == 4) {
+                const bool na = is_nan_bits(a), nb = is_nan_bits(b);
+                v = (!na && !nb) ? nan_like_x86(a * b, a, b) : (!na ? a : (!nb ? b : 0.0f));
+              } else v = nan_like_x86((float)((double)(a + b) * 0.5), a, b);
+              ba.outp[((size_t)gz * ny + gy) * nx + gx] = v;
+            }
           }
+      };
+      // Regular chunk (the usual case: both maps advance one source plane per output plane, rows
+      // and columns unit-stride): after the first two planes every z step takes exactly one new
+      // plane per map, and the two plane buffers swap roles by unrolling -- no table-driven
+      // branching, no register moves.  Same arithmetic as the general loop below.
+      const bool lean = ca.unit && cb.unit && chunk_regular(tAz, za, zb) && chunk_regular(tBz, za, zb);
+      if (lean) {
+        float pa[Y], qa[Y], pb[Y], qb[Y], va[Y], vb[Y];
+        consumer_take<Y, true>(ca, ringA, fullA, emptyA, cntA, plane_floats, pa);
+        consumer_take<Y, true>(cb, ringB, fullB, emptyB, cntB, plane_floats, pb);
+        auto step = [&](int gz, const float (&la)[Y], float (&ha)[Y], const float (&lb)[Y], float (&hb)[Y]) {
+          const float fa = tAz[gz].f, fb = tBz[gz].f;
+          consumer_take<Y, true>(ca, ringA, fullA, emptyA, cntA, plane_floats, ha);
+          consumer_take<Y, true>(cb, ringB, fullB, emptyB, cntB, plane_floats, hb);
+#pragma unroll
+          for (int r = 0; r < Y; ++r) {
+            va[r] = la[r] + fa * (ha[r] - la[r]);
+            vb[r] = lb[r] + fb * (hb[r] - lb[r]);
+          }
+          emit(gz, va, vb);
+        };
+        int gz = za;
+        for (; gz + 1 < zb; gz += 2) {
+          step(gz, pa, qa, pb, qb);
+          step(gz + 1, qa, pa, qb, pb);
+        }
+        if (gz < zb) step(gz, pa, qa, pb, qb);
+      } else {
+        for (int gz = za; gz < zb; ++gz) {
+          const AxisEntry az = tAz[gz], bz = tBz[gz];
+          float va[Y], vb[Y];
+          consumer_sample<Y>(ca, az, ringA, fullA, emptyA, cntA, plane_floats, va);
+          consumer_sample<Y>(cb, bz, ringB, fullB, emptyB, cntB, plane_floats, vb);
+          emit(gz, va, vb);
         }
       }
     }

@@ -180,9 +180,9 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
     const unsigned int *__restrict__ list = tlist + ((size_t)p * tiles_cap + local) * cap_t;
     const int n = min(tcount[(size_t)p * tiles_cap + local], cap_t);
 
-    float acc[8];
+    f32x2 acc[4];  // 8 consecutive x as four packed pairs
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+    for (int k = 0; k < 4; ++k) acc[k] = pack2(0.0f, 0.0f);
 
     auto process = [&](int m) {
       if (lane < m) {
@@ -229,12 +229,11 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
         const float d2 = r[8 + ly] + r[16 + lz];                                  // dy*dy + dz*dz
         const float2 c2 = *reinterpret_cast<const float2 *>(r + 20);              // arinv, radlim^2
         const float e = (d2 < c2.y) ? ex2_approx2(d2 * c2.x) : 0.0f;              // !(dy2dz2 >= radlim2)
-        const float4 e0 = *reinterpret_cast<const float4 *>(r);
-        const float4 e1 = *reinterpret_cast<const float4 *>(r + 4);
-        acc[0] = __fmaf_rn(e0.x, e, acc[0]); acc[1] = __fmaf_rn(e0.y, e, acc[1]);
-        acc[2] = __fmaf_rn(e0.z, e, acc[2]); acc[3] = __fmaf_rn(e0.w, e, acc[3]);
-        acc[4] = __fmaf_rn(e1.x, e, acc[4]); acc[5] = __fmaf_rn(e1.y, e, acc[5]);
-        acc[6] = __fmaf_rn(e1.z, e, acc[6]); acc[7] = __fmaf_rn(e1.w, e, acc[7]);
+        const ulonglong2 e0 = *reinterpret_cast<const ulonglong2 *>(r);
+        const ulonglong2 e1 = *reinterpret_cast<const ulonglong2 *>(r + 4);
+        const f32x2 ee = pack2(e, e);
+        acc[0] = fma2(e0.x, ee, acc[0]); acc[1] = fma2(e0.y, ee, acc[1]);
+        acc[2] = fma2(e1.x, ee, acc[2]); acc[3] = fma2(e1.y, ee, acc[3]);
       };
       int a = 0;
       for (; a + 2 <= m; a += 2) {
@@ -272,9 +271,12 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
     const int Y = Y0 + ly, Z = Z0 + lz;
     if (Y < nv1 && Z < nv2) {
       float *row = grid_all + (size_t)p * cap_grid + ((size_t)Z * nv1 + Y) * nv0;
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) unpack2(acc[k], o[2 * k], o[2 * k + 1]);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        if (X0 + k < nv0) row[X0 + k] = acc[k];
+        if (X0 + k < nv0) row[X0 + k] = o[k];
     }
   }
 }
