@@ -208,6 +208,33 @@ def test_binary_ops_staged_ring_path_bit_exact(oracle, monkeypatch):
                 assert np.array_equal(bits(got.data), bits(want)), (op, use_union)
 
 
+def test_binary_ops_identity_stream_path_bit_exact(oracle, monkeypatch):
+    """two-map ops on one exact lattice stream without interpolation; -0 voxels (whose sampled sign
+    depends on their neighbours) are redone literally, NaN/inf/huge values send the op back to the
+    interpolating path: every result bit-exact"""
+    r = np.random.default_rng(22)
+    cases = [(OGrid.make((0, 0, 0), (96, 70, 50), 1.0), OGrid.make((0, 0, 0), (96, 70, 50), 1.0)),
+             (OGrid.make((0, 0, 0), (40, 36, 32), 1.0), OGrid.make((-4, -8, -2), (64, 60, 56), 1.0)),
+             (OGrid.make((2, 2, 2), (37, 21, 19), 2.0), OGrid.make((2, 2, 2), (37, 21, 19), 2.0))]
+    monkeypatch.setenv("VOLTOOL_CC_STAGED", "1")
+    for A, B in cases:
+        a, b = r.random(A.n, dtype=np.float32) - 0.3, r.random(B.n, dtype=np.float32) - 0.3
+        a[::7] = 0.0
+        a[::11] = -0.0
+        b[::13] = -0.0
+        b[5::17] = 0.0
+        for poison in (None, np.nan, np.inf, 3.0e38):
+            a2 = a.copy()
+            if poison is not None:
+                a2[3::1009] = poison
+            for op in range(4):
+                for use_union in (False, True):
+                    og, want = oracle.binary(op, A, a2, B, b, True, use_union)
+                    got = vt.binary(op, vt.VolMap(G(A), a2), vt.VolMap(G(B), b), True, use_union)
+                    assert got.grid.astuple() == og.astuple()
+                    assert np.array_equal(bits(got.data), bits(want)), (op, use_union, poison)
+
+
 # ------------------------------------------------------------------------------------------ unary + stats
 def test_unary_sequence_bit_exact(oracle):
     g = OGrid.make((1.0, 2.0, 3.0), (22, 17, 19), 1.25)

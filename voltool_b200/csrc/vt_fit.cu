@@ -289,12 +289,22 @@ int vt_fit_eval_poses(vt_fit_ctx *f, const float com[3], const vt_pose *poses, l
 int vt_fit_eval_poses_device(vt_fit_ctx *f, const float com[3], const vt_pose *d_poses, long nposes, float *d_cc) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
+  if (f->pb.use_lists) VT_CUDA(cudaMemsetAsync(f->pb.d_totals + 2, 0, sizeof(int), c.stream));
   for (long p0 = 0; p0 < nposes; p0 += f->B) {
     const int n = (int)std::min<long>(f->B, nposes - p0);
     prep_from_pose_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(d_poses + p0, n, f->pb.d_prep);
     VT_LAUNCHED();
     int rc = eval_prepared(f, com, f->pb.d_prep, n, d_cc + p0);
     if (rc) return rc;
+  }
+  if (f->pb.use_lists) {  // one 4-byte readback per call: a truncated tile list must never go unnoticed
+    int ovf = 0;
+    int rc = batch_lists_overflowed(f->pb, &ovf);
+    if (rc) return rc;
+    if (ovf) {
+      f->pb.use_lists = false;
+      return vt_fit_eval_poses_device(f, com, d_poses, nposes, d_cc);
+    }
   }
   return 0;
 }

@@ -21,16 +21,15 @@ struct MapMarch {
   const float *__restrict__ d;
   long pstride;
   // per thread (x)
-  int dx;                 // x1 - x0: 1, or 0 where the neighbour is clamped onto x0
+  int x0, x1;
   float xf;
   unsigned int loadmask;  // bit 2r: row r0[r] must be loaded, bit 2r+1: row r1[r] (else reuse)
-  // per output row: byte offset of (x0, source row) inside a plane (planes < 4 GiB)
-  unsigned int o0[Y], o1[Y];
+  // per output row (warp-uniform)
+  int r0[Y], r1[Y];   // row offsets inside a plane (< 2^31 voxels per plane)
   float yf[Y];
-  // plane cache: two buffers that swap roles (lower / upper plane) without moving data
-  int zA, zB;
-  float bufA[Y], bufB[Y];
-  int par;                // 0: bufA is the lower plane, 1: bufB is
+  // plane cache
+  int z0, z1;
+  float lo[Y], hi[Y];
 };
 
 template <int Y>
@@ -38,51 +37,38 @@ __device__ __forceinline__ void march_init(MapMarch<Y> &m, const float *d, int n
                                            const AxisEntry *__restrict__ ty, int gy0, int ny_out) {
   m.d = d;
   m.pstride = (long)nx_src * ny_src;
-  m.dx = ex.i1 - ex.i0; m.xf = ex.f;
-  int r0[Y], r1[Y];
+  m.x0 = ex.i0; m.x1 = ex.i1; m.xf = ex.f;
 #pragma unroll
   for (int r = 0; r < Y; ++r) {
     const int gy = min(gy0 + r, ny_out - 1);
     const AxisEntry ey = ty[gy];
-    r0[r] = ey.i0 * nx_src;
-    r1[r] = ey.i1 * nx_src;
+    m.r0[r] = ey.i0 * nx_src;
+    m.r1[r] = ey.i1 * nx_src;
     m.yf[r] = ey.f;
   }
   m.loadmask = 0u;
 #pragma unroll
   for (int r = 0; r < Y; ++r) {
-    if (r == 0 || r0[r] != r1[r - 1]) m.loadmask |= 1u << (2 * r);
-    if (r1[r] != r0[r]) m.loadmask |= 1u << (2 * r + 1);
-    m.o0[r] = 4u * (unsigned int)(r0[r] + ex.i0);
-    m.o1[r] = 4u * (unsigned int)(r1[r] + ex.i0);
+    if (r == 0 || m.r0[r] != m.r1[r - 1]) m.loadmask |= 1u << (2 * r);
+    if (m.r1[r] != m.r0[r]) m.loadmask |= 1u << (2 * r + 1);
   }
-  m.zA = -1; m.zB = -1; m.par = 0;
+  m.z0 = -1; m.z1 = -1;
 }
 
 // Bilinear values of plane z for the Y rows.  Both x neighbours are plain loads (they share a
 // sector almost always; L1 serves the second): a shuffle would save the request but costs a
 // WARPSYNC/collective pair per row in SASS.  All loads of the plane are issued before the first
-// lerp; which rows need loading is warp-uniform (m.loadmask).  Addresses are one 64-bit plane
-// base plus hoisted 32-bit offsets.
+// lerp; which rows need loading is warp-uniform (m.loadmask).
 template <int Y>
 __device__ __forceinline__ void march_plane(const MapMarch<Y> &m, int z, float (&out)[Y]) {
-  // the two plane bases are materialised once (the empty asm keeps the compiler from folding the
-  // 64-bit plane term into every load's address); each load then adds a 32-bit byte offset
-  unsigned long long P0 = (unsigned long long)(m.d + (long)z * m.pstride);
-  unsigned long long P1 = P0 + 4ull * (unsigned int)m.dx;
-  asm volatile("" : "+l"(P0), "+l"(P1));
+  const float *__restrict__ P0 = m.d + (long)z * m.pstride + m.x0;
+  const float *__restrict__ P1 = m.d + (long)z * m.pstride + m.x1;
   float a0[Y], a1[Y], b0[Y], b1[Y];
 #pragma unroll
   for (int r = 0; r < Y; ++r) {
     a0[r] = a1[r] = b0[r] = b1[r] = 0.f;
-    if ((m.loadmask >> (2 * r)) & 1) {
-      a0[r] = __ldg(reinterpret_cast<const float *>(P0 + m.o0[r]));
-      a1[r] = __ldg(reinterpret_cast<const float *>(P1 + m.o0[r]));
-    }
-    if ((m.loadmask >> (2 * r + 1)) & 1) {
-      b0[r] = __ldg(reinterpret_cast<const float *>(P0 + m.o1[r]));
-      b1[r] = __ldg(reinterpret_cast<const float *>(P1 + m.o1[r]));
-    }
+    if ((m.loadmask >> (2 * r)) & 1) { a0[r] = __ldg(P0 + m.r0[r]); a1[r] = __ldg(P1 + m.r0[r]); }
+    if ((m.loadmask >> (2 * r + 1)) & 1) { b0[r] = __ldg(P0 + m.r1[r]); b1[r] = __ldg(P1 + m.r1[r]); }
   }
   float prev_xl = 0.f;
 #pragma unroll
@@ -96,34 +82,25 @@ __device__ __forceinline__ void march_plane(const MapMarch<Y> &m, int z, float (
   }
 }
 
-// one z step with buffer roles fixed at compile time (P = 1: bufB is the lower plane)
-template <int Y, int P>
-__device__ __forceinline__ void march_step(MapMarch<Y> &m, const AxisEntry &ez, float (&v)[Y]) {
-  float(&lo)[Y] = P ? m.bufB : m.bufA;
-  float(&hi)[Y] = P ? m.bufA : m.bufB;
-  int &zlo = P ? m.zB : m.zA;
-  int &zhi = P ? m.zA : m.zB;
-  if (ez.i0 != zlo) { march_plane(m, ez.i0, lo); zlo = ez.i0; }
-  if (ez.i1 == zlo) {
-#pragma unroll
-    for (int r = 0; r < Y; ++r) hi[r] = lo[r];
-    zhi = zlo;
-  } else if (ez.i1 != zhi) {
-    march_plane(m, ez.i1, hi);
-    zhi = ez.i1;
-  }
-#pragma unroll
-  for (int r = 0; r < Y; ++r) v[r] = lo[r] + ez.f * (hi[r] - lo[r]);
-}
-
 // values of the Y rows at the output z whose table entry is ez (ez.inside must hold)
 template <int Y>
 __device__ __forceinline__ void march_sample(MapMarch<Y> &m, const AxisEntry &ez, float (&v)[Y]) {
-  // the usual advance: the upper plane becomes the lower one -- the buffers swap roles
-  const int zlo = m.par ? m.zB : m.zA, zhi = m.par ? m.zA : m.zB;
-  if (ez.i0 == zhi && ez.i0 != zlo) m.par ^= 1;
-  if (m.par) march_step<Y, 1>(m, ez, v);
-  else march_step<Y, 0>(m, ez, v);
+  if (ez.i0 == m.z1 && ez.i0 != m.z0) {  // the usual advance: upper plane becomes the lower one
+#pragma unroll
+    for (int r = 0; r < Y; ++r) { const float t = m.lo[r]; m.lo[r] = m.hi[r]; m.hi[r] = t; }
+    const int t = m.z0; m.z0 = m.z1; m.z1 = t;
+  }
+  if (ez.i0 != m.z0) { march_plane(m, ez.i0, m.lo); m.z0 = ez.i0; }
+  if (ez.i1 == m.z0) {
+#pragma unroll
+    for (int r = 0; r < Y; ++r) m.hi[r] = m.lo[r];
+    m.z1 = m.z0;
+  } else if (ez.i1 != m.z1) {
+    march_plane(m, ez.i1, m.hi);
+    m.z1 = ez.i1;
+  }
+#pragma unroll
+  for (int r = 0; r < Y; ++r) v[r] = m.lo[r] + ez.f * (m.hi[r] - m.lo[r]);
 }
 
 // smallest float T with (double)v >= thr  <=>  v >= T for every float v (MDFF.C:77 compares the
