@@ -249,10 +249,11 @@ __global__ void __launch_bounds__(256) blur_xy_kernel(const float *__restrict__ 
     sdst[it] = row * kXT + sx0;
     edge[it] = xs < 0 || xs + 4 * NQ > nx;
   }
-  const int x = tid & 31, yb = (tid >> 5) * 8;
-  const int gx = tx0 + x;
-  const bool colok = gx < nx;
-  const int rows_ok = min(8, ny - (ty0 + yb));   // outputs of this thread that are inside the map
+  // y phase: a thread owns two adjacent columns (one packed pair) and four rows
+  const int xp = (tid & 15) * 2, yb = (tid >> 4) * 4;
+  const int gx = tx0 + xp;
+  const bool colok = gx < nx;                      // nx is a multiple of 4: the pair is in or out together
+  const int rows_ok = min(4, ny - (ty0 + yb));    // outputs of this thread that are inside the map
   const long ooff = (long)(ty0 + yb) * nx + gx;
   int buf = 0;
   for (int z = z0; z < z1; ++z, buf ^= 1) {
@@ -294,16 +295,18 @@ __global__ void __launch_bounds__(256) blur_xy_kernel(const float *__restrict__ 
       *reinterpret_cast<float4 *>(sx + sdst[it]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
     __syncthreads();   // one barrier per plane: the other buffer is only rewritten after the next one
-    float v[8 + 2 * R];
+    f32x2 v[4 + 2 * R];
 #pragma unroll
-    for (int t = 0; t < 8 + 2 * R; ++t) v[t] = sx[(yb + t) * kXT + x];
+    for (int t = 0; t < 4 + 2 * R; ++t) v[t] = *reinterpret_cast<const f32x2 *>(sx + (yb + t) * kXT + xp);
     float *dst = out + (long)z * nxy + ooff;
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      float a = 0.0f;
+    for (int s = 0; s < 4; ++s) {
+      f32x2 a = pack2(0.0f, 0.0f);
 #pragma unroll
-      for (int k = 0; k <= 2 * R; ++k) a = __fmaf_rn(c_taps[k], v[s + k], a);
-      if (colok && s < rows_ok) dst[s * nx] = a;
+      for (int k = 0; k <= 2 * R; ++k) a = fma2(pack2(c_taps[k], c_taps[k]), v[s + k], a);   // FFMA2, taps in order
+      float a0, a1;
+      unpack2(a, a0, a1);
+      if (colok && s < rows_ok) *reinterpret_cast<float2 *>(dst + s * nx) = make_float2(a0, a1);
     }
   }
 }
