@@ -105,6 +105,15 @@ int vt_histogram(vt_map *m, int nbins, long *bins, float *midpts);    /* histogr
 int vt_vol_moveto(vt_map *m, const float com[3], const float pos[3]); /* vol_moveto, Voltool.C:379-391 */
 int vt_vol_move(vt_map *m, const float mat[16]);                       /* vol_move, Voltool.C:399-438 */
 
+/* ---------------------------------------------------------------- map files
+ * OpenDX scalar fields as VMD's volmap_write_dx_file produces them (call sites TclMDFF.C:146,159,538;
+ * the writer is not in the snapshot: layout restated -- z fastest on disk, x fastest in memory).
+ * vt_dx_* work on host arrays and need no GPU; vt_dx_read mallocs *data (release: vt_free_host). */
+int vt_dx_write(const char *path, const vt_grid *g, const float *data, const char *name);
+int vt_dx_read(const char *path, vt_grid *g, float **data);
+int vt_map_write_dx(const vt_map *m, const char *path, const char *name);  /* `-o <file>` of sim/cc, TclMDFF.C:159 */
+int vt_map_read_dx(const char *path, vt_map **out);                         /* `-i <input map>`, TclMDFF.C:176 */
+
 /* ---------------------------------------------------------------- resizing ops (replace data) */
 int vt_pad(vt_map *m, int padxm, int padxp, int padym, int padyp, int padzm, int padzp); /* ::pad :542-609; trim = pad(-t) TclVoltool.C:1185 */
 int vt_crop(vt_map *m, double minx, double miny, double minz, double maxx, double maxy, double maxz); /* ::crop :615-631 */

@@ -447,3 +447,47 @@ def test_vol_move_moveto(oracle):
         m = vt.VolMap(G(g), d).vol_move(mat)
         assert m.grid.astuple() == oracle.vol_move(g, mat).astuple()
         assert np.array_equal(bits(m.data), bits(d))
+
+
+def test_map_dx_files(tmp_path):
+    g = vt.Grid.make((0.5, -2.0, 3.0), (12, 9, 7), (1.0, 1.5, 0.75))
+    a = rng_map(31, g.n)
+    A = vt.VolMap(g, a)
+    A.gaussian_blur(1.0)
+    p = str(tmp_path / "blur.dx")
+    A.write_dx(p, "smoothed")
+    B = vt.VolMap.read_dx(p)
+    assert np.array_equal(bits(A.data), bits(B.data))
+    assert A.datarange() == B.datarange()          # the min/max cache is rebuilt on load
+    assert abs(vt.cc_threaded(A, B) - 1.0) < 1e-9
+
+
+def test_cli_commands_match_api(tmp_path, capsys):
+    """the Tcl-free front end (python -m voltool_b200 ...) drives the same entry points"""
+    from voltool_b200 import cli
+    g = vt.Grid.make((0, 0, 0), (24, 20, 16), 1.0)
+    a, b = rng_map(41, g.n), rng_map(42, g.n)
+    pa, pb, po = (str(tmp_path / n) for n in ("a.dx", "b.dx", "o.dx"))
+    vt.write_dx(pa, g, a)
+    vt.write_dx(pb, g, b)
+    assert cli.main(["smooth", "-sigma", "1.5", "-i", pa, "-o", po]) == 0
+    want = vt.VolMap(g, a).gaussian_blur(1.5).data
+    assert np.array_equal(bits(vt.read_dx(po)[1]), bits(want))
+    assert cli.main(["trim", "-amt", "1 2 0 1 3 0", "-i", pa, "-o", po]) == 0
+    T = vt.VolMap(g, a); T.pad(-1, -2, 0, -1, -3, 0)
+    g2, d2 = vt.read_dx(po)
+    assert (g2.xsize, g2.ysize, g2.zsize) == (T.grid.xsize, T.grid.ysize, T.grid.zsize) and np.array_equal(bits(d2), bits(T.data))
+    assert cli.main(["add", "-i1", pa, "-i2", pb, "-o", po]) == 0
+    assert np.array_equal(bits(vt.read_dx(po)[1]), bits(vt.add(vt.VolMap(g, a), vt.VolMap(g, b)).data))
+    capsys.readouterr()
+    assert cli.main(["correlate", "-i1", pa, "-i2", pb]) == 0
+    assert abs(float(capsys.readouterr().out) - vt.cc_threaded(vt.VolMap(g, a), vt.VolMap(g, b))) < 1e-8
+    # atoms: sim -> cc against its own map is 1
+    pos, radii, mass = make_structure(300, 8.0, seed=7)
+    pt, ps = str(tmp_path / "atoms.txt"), str(tmp_path / "sim.dx")
+    cli.write_atoms(pt, pos, radii, mass)
+    assert cli.main(["sim", "-atoms", pt, "-res", "5", "-o", ps]) == 0
+    capsys.readouterr()
+    assert cli.main(["cc", "-atoms", pt, "-res", "5", "-i", ps]) == 0
+    assert abs(float(capsys.readouterr().out) - 1.0) < 1e-6
+    assert cli.main(["smooth", "-i", pa]) == 1          # -sigma missing: usage error, nothing written

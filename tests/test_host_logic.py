@@ -196,3 +196,71 @@ def test_table_merge_roundtrip_single_process():
         for r in range(world):
             out[r::world] = shards[r][:out[r::world].size]
         assert np.array_equal(out, tab)
+
+
+# ------------------------------------------------------------------------------------------ .dx files (host only)
+def test_dx_round_trip_and_layout(tmp_path):
+    """OpenDX files: z fastest on disk, x fastest in memory; every float (incl. nan/inf, -0) survives"""
+    import voltool_b200 as vt
+    g = vt.Grid.make((-3.25, 1.5, 0.125), (5, 4, 3), (1.06, 0.5, 2.0))
+    a = np.random.default_rng(5).standard_normal(g.n).astype(np.float32)
+    a[3], a[7], a[11], a[13] = np.nan, np.inf, -np.inf, -0.0
+    path = str(tmp_path / "m.dx")
+    vt.write_dx(path, g, a, name="test map")
+    g2, b = vt.read_dx(path)
+    assert (g2.xsize, g2.ysize, g2.zsize) == (5, 4, 3)
+    for k in range(3):
+        assert g2.origin[k] == g.origin[k]
+        assert abs(g2.xaxis[k] - g.xaxis[k]) <= 1e-15 * max(1.0, abs(g.xaxis[k]))
+        assert abs(g2.yaxis[k] - g.yaxis[k]) <= 1e-15 * max(1.0, abs(g.yaxis[k]))
+        assert abs(g2.zaxis[k] - g.zaxis[k]) <= 1e-15 * max(1.0, abs(g.zaxis[k]))
+    assert np.array_equal(a.view(np.uint32)[~np.isnan(a)], b.view(np.uint32)[~np.isnan(a)])
+    assert np.isnan(b[3])
+    # layout: the first value on disk is voxel (0,0,0), the second (x=0,y=0,z=1)
+    lines = open(path).read().splitlines()
+    i = [k for k, ln in enumerate(lines) if "data follows" in ln][0]
+    first = lines[i + 1].split()
+    assert np.float32(first[0]) == a[0] and np.float32(first[1]) == a[1 * 4 * 5]
+    assert "counts 5 4 3" in lines[1] and lines[-1] == 'object "test map" class field'
+    # a file as VMD writes it (three values per line, %g, trailing partial line)
+    vmd = str(tmp_path / "vmd.dx")
+    open(vmd, "w").write("# Data calculated by the VMD volmap function\n"
+                         "object 1 class gridpositions counts 2 2 2\norigin 1 2 3\n"
+                         "delta 0.5 0 0\ndelta 0 0.5 0\ndelta 0 0 0.5\n"
+                         "object 2 class gridconnections counts 2 2 2\n"
+                         "object 3 class array type double rank 0 items 8 data follows\n"
+                         "0 1 2\n3 4 5\n6 7\n\nobject \"density\" class field\n")
+    g3, c = vt.read_dx(vmd)
+    assert g3.xaxis[0] == 0.5 and g3.origin[2] == 3.0
+    # disk index = x*4 + y*2 + z  ->  memory index = z*4 + y*2 + x
+    want = np.zeros(8, np.float32)
+    for x in range(2):
+        for y in range(2):
+            for z in range(2):
+                want[z * 4 + y * 2 + x] = x * 4 + y * 2 + z
+    assert np.array_equal(c, want)
+    # errors are reported, not swallowed
+    bad = str(tmp_path / "bad.dx")
+    open(bad, "w").write("object 1 class gridpositions counts 2 2 2\norigin 0 0 0\n")
+    with pytest.raises(vt.VoltoolGpuError):
+        vt.read_dx(bad)
+
+
+def test_cli_option_parsing():
+    """Tcl-style lists may be quoted, braced or spread over words; unknown options are errors"""
+    from voltool_b200 import cli
+    o, pos = cli.parse("trim", ["-i", "a.dx", "-amt", "1 2 3 4 5 6", "-o", "b.dx"])
+    assert o["-amt"] == ["1", "2", "3", "4", "5", "6"] and o["-i"] == "a.dx" and o["-o"] == "b.dx"
+    o, _ = cli.parse("crop", ["-amt", "{-1", "2.5", "3", "4", "5", "6}", "-i", "a.dx"])
+    assert [float(v) for v in o["-amt"]] == [-1, 2.5, 3, 4, 5, 6]
+    o, _ = cli.parse("smult", ["-amt", "-2.5", "-i", "a.dx"])
+    assert float(o["-amt"]) == -2.5
+    o, pos = cli.parse("info", ["minmax", "-i", "a.dx"])
+    assert pos == ["minmax"]
+    o, _ = cli.parse("add", ["-i1", "a.dx", "-i2", "b.dx", "-union", "-nointerp"])
+    assert o["-union"] is True and o["-nointerp"] is True
+    with pytest.raises(cli.UsageError):
+        cli.parse("smooth", ["-sgima", "2"])
+    with pytest.raises(cli.UsageError):
+        cli.parse("range", ["-minmax", "1"])
+    assert cli.main([]) == 1 and cli.main(["help"]) == 0

@@ -145,6 +145,10 @@ def lib():
     L.vt_binary.argtypes = [C.c_int, C.c_int, C.c_int, M, M, C.POINTER(M)]
     L.vt_binary_host.argtypes = [C.c_int, C.c_int, C.c_int, G, C.c_void_p, G, C.c_void_p, G, C.POINTER(c_float_p)]
     L.vt_free_host.argtypes = [C.c_void_p]
+    L.vt_dx_write.argtypes = [C.c_char_p, G, C.c_void_p, C.c_char_p]
+    L.vt_dx_read.argtypes = [C.c_char_p, G, C.POINTER(c_float_p)]
+    L.vt_map_write_dx.argtypes = [M, C.c_char_p, C.c_char_p]
+    L.vt_map_read_dx.argtypes = [C.c_char_p, C.POINTER(M)]
     L.vt_init_from_intersection.argtypes = [G, G, G]
     L.vt_init_from_union.argtypes = [G, G, G]
     L.vt_sim_policy.argtypes = [C.c_double, C.c_double, c_float_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -311,6 +315,17 @@ class VolMap:
         _check(lib().vt_map_upload(self.h, _vp(data)), "vt_map_upload")
 
     # ---- VolumetricData methods ------------------------------------------------------------------
+    def write_dx(self, path, name="density"):
+        _need()
+        _check(lib().vt_map_write_dx(self.h, os.fsencode(path), name.encode()), "vt_map_write_dx")
+
+    @classmethod
+    def read_dx(cls, path):
+        _need()
+        h = C.c_void_p()
+        _check(lib().vt_map_read_dx(os.fsencode(path), C.byref(h)), "vt_map_read_dx")
+        return cls(_handle=h)
+
     def clamp(self, lo, hi):
         _check(lib().vt_clamp(self.h, lo, hi), "vt_clamp"); return self
 
@@ -384,6 +399,26 @@ class VolMap:
 
 
 # ---- free functions ------------------------------------------------------------------------------
+def write_dx(path, grid, data, name="density"):
+    """host arrays -> OpenDX file (no GPU needed); VMD volmap layout, TclMDFF.C:159"""
+    d = f32(data)
+    if d.size != grid.n:
+        raise ValueError("data size does not match the grid")
+    _check(lib().vt_dx_write(os.fsencode(path), C.byref(grid), _vp(d), name.encode()), "vt_dx_write")
+
+
+def read_dx(path):
+    """OpenDX file -> (Grid, float32 array in map order: x fastest); no GPU needed"""
+    g = Grid()
+    p = c_float_p()
+    _check(lib().vt_dx_read(os.fsencode(path), C.byref(g), C.byref(p)), "vt_dx_read")
+    try:
+        out = np.ctypeslib.as_array(p, shape=(max(g.n, 1),))[:g.n].copy()
+    finally:
+        lib().vt_free_host(p)
+    return g, out
+
+
 def cc_threaded(qs_vol, target_vol, threshold=-FLT_MAX, full=False):
     """cc_threaded(qsVol, targetVol, &cc, threshold)  MDFF.C:102"""
     cc, n, sums = C.c_double(), C.c_long(), (C.c_double * 5)()
