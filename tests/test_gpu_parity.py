@@ -327,6 +327,18 @@ def test_down_super_sample_bit_exact(oracle, size):
     assert np.array_equal(bits(m3.data), bits(want3))
 
 
+def test_supersample_single_kernel_bit_exact(oracle, monkeypatch):
+    """the one-kernel form (default for large maps) against the oracle on ragged sizes"""
+    monkeypatch.setenv("VOLTOOL_SUPERSAMPLE_FUSED", "1")
+    for size in [(70, 9, 67), (3, 3, 3), (65, 17, 130), (129, 8, 5)]:
+        g = OGrid.make((0.5, 1.0, -2.0), size, (1.0, 1.5, 0.5))
+        a = rng_map(61, g.n)
+        og, want = oracle.supersample(g, a)
+        M = vt.VolMap(G(g), a)
+        M.supersample()
+        assert same_grid(M.grid, og) and np.array_equal(bits(M.data), bits(want)), size
+
+
 def test_supersample_known_answers():
     # (-y0 + 5 y1 + 5 y2 - y3)/8 interior stencil; replicated ends give 3/8 on the ramp 0,1,2
     g = vt.Grid.make((0, 0, 0), (6, 3, 3), 1.0)
