@@ -327,16 +327,40 @@ def test_down_super_sample_bit_exact(oracle, size):
     assert np.array_equal(bits(m3.data), bits(want3))
 
 
-def test_supersample_single_kernel_bit_exact(oracle, monkeypatch):
-    """the one-kernel form (default for large maps) against the oracle on ragged sizes"""
-    monkeypatch.setenv("VOLTOOL_SUPERSAMPLE_FUSED", "1")
-    for size in [(70, 9, 67), (3, 3, 3), (65, 17, 130), (129, 8, 5)]:
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_supersample_single_kernel_bit_exact(oracle, monkeypatch, mode):
+    """the one-kernel forms (2 = register z window, the default for large maps; 1 = shared-memory
+    ring) against the oracle on ragged sizes"""
+    monkeypatch.setenv("VOLTOOL_SUPERSAMPLE_FUSED", mode)
+    for size in [(70, 9, 67), (3, 3, 3), (65, 17, 130), (129, 8, 5), (64, 8, 64), (66, 10, 4), (4, 200, 3)]:
         g = OGrid.make((0.5, 1.0, -2.0), size, (1.0, 1.5, 0.5))
         a = rng_map(61, g.n)
         og, want = oracle.supersample(g, a)
         M = vt.VolMap(G(g), a)
         M.supersample()
         assert same_grid(M.grid, og) and np.array_equal(bits(M.data), bits(want)), size
+
+
+def test_supersample_packed_kernel_tiny_values(oracle, monkeypatch):
+    """the packed kernel multiplies by exact powers of two inside fused multiply-adds; that only differs
+    from the reference's separate roundings when a product is subnormal, which it detects (a nonzero
+    |voxel| < 2^-100) and hands to the scalar kernel: subnormal-range maps stay bit-exact too"""
+    monkeypatch.setenv("VOLTOOL_SUPERSAMPLE_FUSED", "2")
+    g = OGrid.make((0, 0, 0), (20, 18, 9), 1.0)
+    rng = np.random.default_rng(77)
+    a = (rng.random(g.n, dtype=np.float32) * np.float32(3e-38)).astype(np.float32)
+    a[::7] = np.float32(1.0e-42)
+    a[::11] = 0.0
+    og, want = oracle.supersample(g, a)
+    M = vt.VolMap(G(g), a)
+    M.supersample()
+    assert same_grid(M.grid, og) and np.array_equal(bits(M.data), bits(want))
+    b = rng.random(g.n, dtype=np.float32)
+    b[5] = np.float32(1.0e-35)   # one tiny voxel in an ordinary map
+    og, want = oracle.supersample(g, b)
+    M = vt.VolMap(G(g), b)
+    M.supersample()
+    assert np.array_equal(bits(M.data), bits(want))
 
 
 def test_supersample_known_answers():

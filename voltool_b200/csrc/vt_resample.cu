@@ -274,6 +274,196 @@ __global__ void __launch_bounds__(kThreads) supersample_fused_kernel(const float
   }
 }
 
+// ---- all three sweeps in one kernel, z window in registers, packed arithmetic -------------------------
+// Same tile as above (64 x 8 source columns/rows -> 128 x 16 outputs, a chunk of source planes), but a
+// thread owns four output rows of two output columns (X, X + 64) for the whole march: per source plane
+// it reads the five staged x-lines it needs, forms its xy-supersampled values (2 copies, 2 cubics per
+// column), keeps the last four planes of them in registers (rotating names, no moves) and writes the
+// even plane and the odd plane between the two middle window planes.  The x-lines are double
+// buffered: one barrier per plane, no shared-memory ring.  Every cubic runs on a packed pair
+// (FADD2 / FMUL2 / FFMA2, sm_100): the two columns of a thread, or two stencils of the x sweep.
+//
+// cubic_half in packed form: the reference's a0*mu*mu2 + a1*mu2 + a2*mu + y1 (VolumetricData.h:224-232)
+// multiplies by exact powers of two, so (a0*.5)*.25 = a0*.125 and the fused multiply-adds round exactly
+// like the separate multiply and add -- unless a product is subnormal.  That cannot happen when every
+// nonzero |voxel| >= 2^-100 (all differences are then multiples of 2^-123); the x sweep checks this on
+// every source voxel it loads and raises `tiny_flag` otherwise, and the caller redoes the map with the
+// scalar kernel.  The order of the sweeps is the reference's (x, then y on x-swept rows, then z).
+__device__ __forceinline__ f32x2 cubic_half2(f32x2 y0, f32x2 y1, f32x2 y2, f32x2 y3, f32x2 c125, f32x2 c25, f32x2 c5) {
+  const f32x2 a0 = add2(sub2(sub2(y3, y2), y0), y1);
+  const f32x2 a1 = sub2(sub2(y0, y1), a0);
+  const f32x2 a2 = sub2(y2, y0);
+  f32x2 s = fma2(a1, c25, mul2(a0, c125));
+  s = fma2(a2, c5, s);
+  return add2(s, y1);
+}
+
+constexpr int kMLines = kSY + 3;
+constexpr int kMPairs = kMLines * kSX / 2;                       // x-sweep items are done two at a time
+constexpr int kMIt = (kMPairs + kThreads - 1) / kThreads;
+constexpr int kRawW = kSX + 3, kRawP = kSX + 4;                   // raw tile: columns tx0-1 .. tx0+kSX+1, row pitch
+constexpr int kRawN = kMLines * kRawW;                            // elements staged per plane
+constexpr int kRawIt = (kRawN + kThreads - 1) / kThreads;
+constexpr int kRawStages = 4;
+
+__device__ __forceinline__ void cp_async4(float *smem_dst, const void *gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 3) supersample_march_kernel(const float *__restrict__ src, int ox, int oy,
+                                                                        int oz, float *__restrict__ dst, int nx, int ny,
+                                                                        int xt, int yt, int *__restrict__ tiny_flag) {
+  __shared__ __align__(16) float lines[2][kMLines * kOX];
+  __shared__ float raw[kRawStages][kMLines * kRawP];
+  const int tid = threadIdx.x;
+  const long w = blockIdx.x;
+  const int tx0 = (int)(w % xt) * kSX, g0 = (int)((w / xt) % yt) * kSY;
+  const int gbeg = (int)(w / ((long)xt * yt)) * kSZ, gend = min(oz, gbeg + kSZ);
+  const int X0 = 2 * tx0, Y0 = 2 * g0;
+  const long oxy = (long)ox * oy, nxy = (long)nx * ny;
+  const int nsteps = gend - gbeg + 3;   // source planes gbeg-1 .. gend+1 (clamped: ends replicated, :878-913)
+  const f32x2 c125 = pack2(0.125f, 0.125f), c25 = pack2(0.25f, 0.25f), c5 = pack2(0.5f, 0.5f);
+
+  // ---- raw-tile staging: every thread copies up to kRawIt source voxels per plane with cp.async, rows and
+  // columns clamped to the map (so the stencils of the x sweep need no edge cases), planes ahead of their use
+  unsigned long long rp[kRawIt];   // source address of the element in the plane staged next
+  int rdst[kRawIt];                // shared-memory slot inside a stage, < 0: none
+#pragma unroll
+  for (int k = 0; k < kRawIt; ++k) {
+    const int e = tid + kThreads * k;
+    const int l = e / kRawW, c = e - l * kRawW;
+    int g = g0 - 1 + l, gx = tx0 - 1 + c;
+    g = g < 0 ? 0 : (g > oy - 1 ? oy - 1 : g);
+    gx = gx < 0 ? 0 : (gx > ox - 1 ? ox - 1 : gx);
+    rdst[k] = e < kRawN ? l * kRawP + c : -1;
+    const int pfirst = gbeg > 0 ? gbeg - 1 : 0;
+    rp[k] = (unsigned long long)(src + (pfirst * oxy + (long)g * ox + gx));
+  }
+  const unsigned long long sstep = (unsigned long long)oxy * sizeof(float);
+  int staged = 0;   // planes issued so far; the next one is p = gbeg - 1 + staged
+  auto stage_plane = [&]() {
+    if (staged < nsteps) {
+      float *buf = raw[staged & (kRawStages - 1)];
+#pragma unroll
+      for (int k = 0; k < kRawIt; ++k)
+        if (rdst[k] >= 0) cp_async4(buf + rdst[k], reinterpret_cast<const void *>(rp[k]));
+      const int p = gbeg - 1 + staged;
+      if (p >= 0 && p < oz - 1) {
+#pragma unroll
+        for (int k = 0; k < kRawIt; ++k) rp[k] += sstep;
+      }
+    }
+    cp_async_commit();
+    ++staged;
+  };
+
+  // ---- x sweep items (two per trip): raw-tile offset of the left stencil sample and the shared-memory slot
+  // of the output pair (2t, 2t+1); slot < 0: the item lies right of the map
+  int roff[kMIt][2], sdst[kMIt][2];
+#pragma unroll
+  for (int it = 0; it < kMIt; ++it)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = tid + kThreads * it;
+      const int idx = (q < kMPairs ? q : 0) + h * kMPairs;
+      const int l = idx / kSX, t = idx - l * kSX;
+      roff[it][h] = l * kRawP + t;
+      sdst[it][h] = (q < kMPairs && tx0 + t < ox) ? l * kOX + 2 * t : -1;
+    }
+  unsigned int tiny = 0;
+  auto x_sweep = [&](int s) {
+    const float *rw = raw[s & (kRawStages - 1)];
+    float *ln = lines[s & 1];
+#pragma unroll
+    for (int it = 0; it < kMIt; ++it) {
+      if (kThreads * it + tid >= kMPairs) continue;
+      const float *ra = rw + roff[it][0], *rb = rw + roff[it][1];
+      const float a1 = ra[1], b1 = rb[1];
+      const f32x2 o = cubic_half2(pack2(ra[0], rb[0]), pack2(a1, b1), pack2(ra[2], rb[2]), pack2(ra[3], rb[3]), c125, c25, c5);
+      float oa, ob;
+      unpack2(o, oa, ob);
+      tiny |= (unsigned int)(((__float_as_uint(a1) & 0x7fffffffu) - 1u) < 0x0d7fffffu);
+      tiny |= (unsigned int)(((__float_as_uint(b1) & 0x7fffffffu) - 1u) < 0x0d7fffffu);
+      if (sdst[it][0] >= 0) *reinterpret_cast<float2 *>(ln + sdst[it][0]) = make_float2(a1, oa);
+      if (sdst[it][1] >= 0) *reinterpret_cast<float2 *>(ln + sdst[it][1]) = make_float2(b1, ob);
+    }
+  };
+
+  // ---- y / z sweeps: output columns X and X + 64, four output rows 4 rg ..
+  const int X = tid & (kSX - 1), rg = tid >> 6;
+  unsigned int smask = 0;   // bit j: row j of column X is inside the map; bit 4 + j: column X + 64
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool rowok = Y0 + 4 * rg + j < ny;
+    if (rowok && X0 + X < nx) smask |= 1u << j;
+    if (rowok && X0 + X + kSX < nx) smask |= 16u << j;
+  }
+  // this thread's four output rows in the even plane 2p of the current step (only dereferenced when
+  // that plane exists); the odd plane written in the same step, 2(p-2)+1, lies 3 planes below
+  unsigned long long oe[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) oe[j] = (unsigned long long)(dst + (2L * (gbeg - 1) * nxy + (long)(Y0 + 4 * rg + j) * nx + X0 + X));
+  const unsigned long long ostep = 2ull * nxy * sizeof(float), oback = 3ull * nxy * sizeof(float);
+  f32x2 A[4], B[4], C[4], D[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) A[j] = B[j] = C[j] = D[j] = 0ull;
+
+  auto plane_step = [&](int s, const f32x2 (&w0)[4], const f32x2 (&w1)[4], const f32x2 (&w2)[4], f32x2 (&w3)[4]) {
+    const int p = gbeg - 1 + s;
+    cp_async_wait<1>();   // this thread's copies of plane s+1 have landed ...
+    __syncthreads();      // ... and everybody's; lines[s&1] is complete; lines[(s+1)&1] and raw[(s+3)&3] are free
+    if (s + 1 < nsteps) x_sweep(s + 1);
+    const float *ln = lines[s & 1];
+    f32x2 L[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) L[k] = pack2(ln[(2 * rg + k) * kOX + X], ln[(2 * rg + k) * kOX + X + kSX]);
+    stage_plane();        // plane s+3
+    w3[0] = L[1];                                               // even output rows: copies (:783-794)
+    w3[2] = L[2];
+    w3[1] = cubic_half2(L[0], L[1], L[2], L[3], c125, c25, c5);  // odd rows (:841-875)
+    w3[3] = cubic_half2(L[1], L[2], L[3], L[4], c125, c25, c5);
+    if (p >= gbeg && p < gend) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a, b;
+        unpack2(w3[j], a, b);
+        float *o = reinterpret_cast<float *>(oe[j]);
+        if ((smask >> j) & 1u) __stcs(o, a);
+        if ((smask >> (4 + j)) & 1u) __stcs(o + kSX, b);
+      }
+    }
+    const int g = p - 2;   // odd plane 2g+1 from planes g-1, g, g+1, g+2 = p
+    if (g >= gbeg && g < gend && g <= oz - 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a, b;
+        unpack2(cubic_half2(w0[j], w1[j], w2[j], w3[j], c125, c25, c5), a, b);
+        float *o = reinterpret_cast<float *>(oe[j] - oback);
+        if ((smask >> j) & 1u) __stcs(o, a);
+        if ((smask >> (4 + j)) & 1u) __stcs(o + kSX, b);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oe[j] += ostep;
+  };
+  stage_plane(); stage_plane(); stage_plane();
+  cp_async_wait<2>();
+  __syncthreads();
+  x_sweep(0);
+  int s = 0;
+  while (true) {
+    plane_step(s, A, B, C, D); if (++s >= nsteps) break;
+    plane_step(s, B, C, D, A); if (++s >= nsteps) break;
+    plane_step(s, C, D, A, B); if (++s >= nsteps) break;
+    plane_step(s, D, A, B, C); if (++s >= nsteps) break;
+  }
+  if (tiny) atomicOr(tiny_flag, 1);
+}
+
 int k_supersample(const float *src, int ox, int oy, int oz, float *dst) {
   VT_REQUIRE_CTX();
   if (ox < 3 || oy < 3 || oz < 3) { set_error("vt_supersample: every dimension must be >= 3"); return 1; }
@@ -284,7 +474,30 @@ int k_supersample(const float *src, int ox, int oy, int oz, float *dst) {
   // measured on B200: the single kernel wins once the intermediate even planes no longer fit L2
   // (512^3 -> 1023^3: 2.06 vs 2.51 ms); below that the two-pass form is as fast or faster
   const char *mode = getenv("VOLTOOL_SUPERSAMPLE_FUSED");
-  if (mode ? atoi(mode) != 0 : (long)ox * oy * oz >= (48L << 20)) {
+  const int fused = mode ? atoi(mode) : ((long)ox * oy * oz >= (48L << 20) ? 2 : 0);
+  if (fused == 2 && (long)ox * oy <= 0x7fffffffL - 4) {
+    const int xt = (ox + kSX - 1) / kSX, yt = (oy + kSY - 1) / kSY;
+    const long work = (long)xt * yt * ((oz + kSZ - 1) / kSZ);
+    if (work <= 0x7fffffffL) {
+      // the packed kernel is exact unless a nonzero voxel is tinier than 2^-100: checked on the device,
+      // such a map is redone below by the scalar kernels
+      static int *d_flag = nullptr, *h_flag = nullptr;
+      if (!d_flag) {
+        VT_CUDA(cudaMalloc((void **)&d_flag, sizeof(int)));
+        VT_CUDA(cudaMallocHost((void **)&h_flag, sizeof(int)));
+      }
+      VT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx().stream));
+      supersample_march_kernel<<<(unsigned int)work, kThreads, 0, ctx().stream>>>(src, ox, oy, oz, dst, nx, ny, xt, yt, d_flag);
+      VT_LAUNCHED();
+      VT_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+      VT_CUDA(cudaStreamSynchronize(ctx().stream));
+      if (*h_flag == 0) {
+        prof_end(PK_RESAMPLE);
+        return 0;
+      }
+    }
+  }
+  if (fused != 0) {   // also the exact fallback of the packed kernel
     const int xt = (ox + kSX - 1) / kSX, yt = (oy + kSY - 1) / kSY;
     const long work = (long)xt * yt * ((oz + kSZ - 1) / kSZ);
     if (work <= 0x7fffffffL) {
