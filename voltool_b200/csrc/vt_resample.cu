@@ -304,7 +304,7 @@ constexpr int kMIt = (kMPairs + kThreads - 1) / kThreads;
 constexpr int kRawW = kSX + 3, kRawP = kSX + 4;                   // raw tile: columns tx0-1 .. tx0+kSX+1, row pitch
 constexpr int kRawN = kMLines * kRawW;                            // elements staged per plane
 constexpr int kRawIt = (kRawN + kThreads - 1) / kThreads;
-constexpr int kRawStages = 4;
+constexpr int kRawStages = 8;                                     // planes in flight: kRawStages - 1
 
 __device__ __forceinline__ void cp_async4(float *smem_dst, const void *gsrc) {
   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
@@ -414,14 +414,14 @@ __global__ void __launch_bounds__(kThreads, 3) supersample_march_kernel(const fl
 
   auto plane_step = [&](int s, const f32x2 (&w0)[4], const f32x2 (&w1)[4], const f32x2 (&w2)[4], f32x2 (&w3)[4]) {
     const int p = gbeg - 1 + s;
-    cp_async_wait<1>();   // this thread's copies of plane s+1 have landed ...
-    __syncthreads();      // ... and everybody's; lines[s&1] is complete; lines[(s+1)&1] and raw[(s+3)&3] are free
+    cp_async_wait<kRawStages - 3>();   // this thread's copies of plane s+1 have landed ...
+    __syncthreads();      // ... and everybody's; lines[s&1] is complete; lines[(s+1)&1] and the oldest raw stage are free
     if (s + 1 < nsteps) x_sweep(s + 1);
     const float *ln = lines[s & 1];
     f32x2 L[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) L[k] = pack2(ln[(2 * rg + k) * kOX + X], ln[(2 * rg + k) * kOX + X + kSX]);
-    stage_plane();        // plane s+3
+    stage_plane();        // plane s + kRawStages - 1
     w3[0] = L[1];                                               // even output rows: copies (:783-794)
     w3[2] = L[2];
     w3[1] = cubic_half2(L[0], L[1], L[2], L[3], c125, c25, c5);  // odd rows (:841-875)
@@ -450,8 +450,9 @@ __global__ void __launch_bounds__(kThreads, 3) supersample_march_kernel(const fl
 #pragma unroll
     for (int j = 0; j < 4; ++j) oe[j] += ostep;
   };
-  stage_plane(); stage_plane(); stage_plane();
-  cp_async_wait<2>();
+#pragma unroll
+  for (int k = 0; k < kRawStages - 1; ++k) stage_plane();
+  cp_async_wait<kRawStages - 2>();
   __syncthreads();
   x_sweep(0);
   int s = 0;
