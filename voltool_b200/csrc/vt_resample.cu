@@ -304,7 +304,7 @@ constexpr int kMIt = (kMPairs + kThreads - 1) / kThreads;
 constexpr int kRawW = kSX + 3, kRawP = kSX + 4;                   // raw tile: columns tx0-1 .. tx0+kSX+1, row pitch
 constexpr int kRawN = kMLines * kRawW;                            // elements staged per plane
 constexpr int kRawIt = (kRawN + kThreads - 1) / kThreads;
-constexpr int kRawStages = 8;                                     // planes in flight: kRawStages - 1
+constexpr int kRawStages = 4;                                     // planes in flight: kRawStages - 1
 
 __device__ __forceinline__ void cp_async4(float *smem_dst, const void *gsrc) {
   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
