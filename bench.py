@@ -326,6 +326,10 @@ def run_ours(args):
             out["cpu_baseline"] = cpu_baseline(pos, radii, com, tmap, poses, budget_s=args.cpu_budget)
         if not args.no_extras:
             out["ops"] = extra_ops(vt, peaks, args)
+            if args.cfg4_map > 0:
+                out["cfg4"] = cfg4_legs(vt, peaks, args.cfg4_map)
+            if args.cfg5_atoms > 0:
+                out["cfg5"] = cfg5_leg(vt, args.cfg5_atoms, args.cfg5_edge)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -419,6 +423,100 @@ def extra_ops(vt, peaks, args):
     dt = (time.perf_counter() - t0) / reps
     res["sim_cc_cfg1"] = {"voxels": S.gridsize(), "s_per_call": dt, "voxels_per_s": S.gridsize() / dt, "cc": cc,
                           "note": "host call incl. atom sort/upload"}
+    return res
+
+
+def cfg4_legs(vt, peaks, n):
+    """BASELINE configs[3] at its own size: correlate + sigma / binmask / add / diff on two n^3 maps
+    (default 1024^3 = 4 GiB each).  The maps are generated on the device (seeds 4001 / 4002) and handed
+    to the library through vt_map_create_from_device; B = 0.7 A + 0.3 U' so the analytic CC is 0.919145."""
+    import torch
+    res = {"map": [n, n, n]}
+    g = vt.Grid.make((0, 0, 0), (n, n, n), 1.0)
+    gen = torch.Generator(device="cuda").manual_seed(4001)
+    a = torch.rand(g.n, generator=gen, device="cuda", dtype=torch.float32)
+    gen.manual_seed(4002)
+    b = torch.rand(g.n, generator=gen, device="cuda", dtype=torch.float32).mul_(0.3).add_(a, alpha=0.7)
+    torch.cuda.synchronize()
+    A = vt.VolMap.from_device(g, a.data_ptr())
+    B = vt.VolMap.from_device(g, b.data_ptr())
+    g_off = vt.Grid.make((0.5, 0, 0), (n, n, n), 1.0)
+    B_off = vt.VolMap.from_device(g_off, b.data_ptr())
+    vt.sync()
+    del a, b
+    torch.cuda.empty_cache()
+
+    def timeit(key, fn, reps=3):
+        fn()
+        vt.profile_reset(); vt.profile_enable(True)
+        for _ in range(reps):
+            fn()
+        ms, cnt = vt.profile_get(key)
+        vt.profile_enable(False)
+        return ms / reps
+
+    def leg(name, key, fn, bytes_per_voxel, **extra):
+        ms = timeit(key, fn)
+        gbs = bytes_per_voxel * g.n / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": bytes_per_voxel, **extra}
+
+    leg("correlate", "cc", lambda: vt.cc_threaded(A, B), 8, cc=vt.cc_threaded(A, B), analytic_cc=0.919145,
+        path="one exact lattice: streamed")
+    leg("correlate_offset", "cc", lambda: vt.cc_threaded(A, B_off), 8, cc=vt.cc_threaded(A, B_off),
+        path="B origin +0.5 voxel in x: shared-memory ring, trilinear")
+    leg("add", "binary", lambda: vt.add(A, B), 12)
+    leg("diff", "binary", lambda: vt.subtract(A, B), 12)
+    leg("add_offset", "binary", lambda: vt.add(A, B_off), 12)
+    del B_off
+    leg("sigma", "stats", lambda: (A.scalar_add(0.0), A.sigma()), 8, note="mean pass + sigma pass, 4 B/voxel each")
+    leg("binmask", "unary", lambda: B.binmask(0.5), 8, note="in place (repeated on the masked map)")
+    del A, B
+    return res
+
+
+def cfg5_leg(vt, natoms, edge):
+    """BASELINE configs[4] on one GPU: ribosome-scale sim (natoms at 3 A into ~edge^3) and a local rigid
+    refinement (+-12 deg in 4 deg steps, then +-3 deg in 1 deg steps about the winner) against a noisy map
+    of a planted nearby pose.  Candidates shard across ranks exactly like the cfg2 search."""
+    from voltool_b200.synth import make_structure, add_noise
+    res = {}
+    ball = 105.0 * (natoms / 250000.0) ** (1 / 3)
+    pos, radii, mass = make_structure(natoms, ball, seed=5001, center=(ball + 12.0,) * 3)
+    radscale, _, quality = vt.sim_policy(3.0)
+    spacing = (2.0 * ball + 8.0) / edge
+    vt.sim(pos, radii, quality, radscale, spacing)        # warm-up (allocations)
+    vt.sync()
+    t0 = time.perf_counter()
+    S = vt.sim(pos, radii, quality, radscale, spacing)
+    vt.sync()
+    dt = time.perf_counter() - t0
+    sg = S.grid
+    pairs = splat_pairs(radii, radscale, spacing)
+    res["sim"] = {"atoms": natoms, "map": [sg.xsize, sg.ysize, sg.zsize], "spacing": spacing, "seconds": dt,
+                  "voxels_per_s": S.gridsize() / dt, "pairs": pairs, "pairs_per_s": pairs / dt,
+                  "note": "vt_sim through the C ABI with host coordinates (sort + upload + splat + min/max)"}
+    com = vt.measure_center(pos, mass)
+    planted = (8.0, -4.0, 5.0)
+    T = vt.sim(vt.pose_apply(pos, com, planted), radii, quality, radscale, spacing)
+    T.upload(add_noise(T.data, 0.02, seed=5002))
+    ctx = vt.FitContext(pos, radii, T, 3.0)
+    lat4 = np.arange(-12.0, 12.1, 4.0)
+    lat1 = np.arange(-3.0, 3.1, 1.0)
+    best = np.zeros(3)
+    n_eval = 0
+    vt.sync()
+    t0 = time.perf_counter()
+    for lat in (lat4, lat1):
+        rot = (best[None, :] + np.stack(np.meshgrid(lat, lat, lat, indexing="ij"), -1).reshape(-1, 3)).astype(np.float32)
+        cc = ctx.eval_poses(com, vt.FitContext.make_poses(rot))
+        best = rot[int(np.nanargmax(cc))].astype(np.float64)
+        n_eval += len(rot)
+        best_cc = float(np.nanmax(cc))
+    dt = time.perf_counter() - t0
+    res["refine"] = {"poses": n_eval, "seconds": dt, "poses_per_s": n_eval / dt, "best_deg": best.tolist(),
+                     "planted_deg": list(planted), "best_cc": best_cc,
+                     "note": "Euler angles about x, y, z compose, so the winner matches the planted triple only approximately"}
+    ctx.close()
     return res
 
 
@@ -554,6 +652,9 @@ def main():
     ap.add_argument("--poses", type=int, default=2048, help="poses per step per GPU")
     ap.add_argument("--ref-poses", type=int, default=4, help="poses per step of the CPU reference arm")
     ap.add_argument("--ops-map", type=int, default=512, help="edge of the maps used by the extra ops legs")
+    ap.add_argument("--cfg4-map", type=int, default=1024, help="edge of the cfg4 maps (0: skip the leg)")
+    ap.add_argument("--cfg5-atoms", type=int, default=250000, help="atoms of the cfg5 leg (0: skip)")
+    ap.add_argument("--cfg5-edge", type=int, default=400, help="target edge of the cfg5 sim grid")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
