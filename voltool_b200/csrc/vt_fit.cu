@@ -8,14 +8,23 @@
 
 using namespace vt;
 
+// Two pose-batch workspaces: while batch i splats and scores on the library stream, batch i+1 is
+// transformed, binned and listed on a second stream (those kernels are small and latency-bound, so
+// they fit into the gaps of the two big ones).
 struct vt_fit_ctx {
   AtomSet as;
-  PoseBatch pb;
+  PoseBatch pb[2];
   const vt_map *target = nullptr;
   float resolution = 0.f;
   double threshold = 0.1;  // calc_cc hard-codes thresholddensity = 0.1 (TclVoltool.C:77)
   int B = 0;
-  PrepPose *h_prep = nullptr;  // pinned staging, B entries
+  int nslots = 2;              // 1: no overlap (VOLTOOL_FIT_OVERLAP=0)
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_front[2] = {nullptr, nullptr}, ev_back[2] = {nullptr, nullptr};
+  PrepPose *h_prep = nullptr;  // pinned staging of the whole call
+  long h_prep_cap = 0;
+  PrepPose *d_prep = nullptr;  // prepared poses of the whole call
+  long d_prep_cap = 0;
   float *d_cc = nullptr;       // results of the current call
   long cc_cap = 0;
 };
@@ -139,12 +148,101 @@ int ensure_cc_buffer(vt_fit_ctx *f, long n) {
   return 0;
 }
 
-// run the pipeline for poses already prepared on the device
-int eval_prepared(vt_fit_ctx *f, const float com[3], const PrepPose *d_prep, int n, float *d_cc) {
-  int rc = batch_prepare(f->as, f->pb, n, d_prep, com, 0, &f->target->grid);
-  if (!rc) rc = batch_splat(f->as, f->pb, n);
-  if (!rc) rc = batch_cc(f->pb, n, f->target, f->threshold, d_cc, nullptr);
+int ensure_prep_buffers(vt_fit_ctx *f, long n, bool host) {
+  if (n > f->d_prep_cap) {
+    dev_free(f->d_prep);
+    f->d_prep = nullptr;
+    if (dev_alloc((void **)&f->d_prep, sizeof(PrepPose) * (size_t)n)) return 2;
+    f->d_prep_cap = n;
+  }
+  if (host && n > f->h_prep_cap) {
+    if (f->h_prep) cudaFreeHost(f->h_prep);
+    f->h_prep = nullptr;
+    cudaError_t e = cudaMallocHost((void **)&f->h_prep, sizeof(PrepPose) * (size_t)n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+    f->h_prep_cap = n;
+  }
+  return 0;
+}
+
+struct StreamScope {   // the launch wrappers use ctx().stream: point it at the second stream for a while
+  cudaStream_t saved;
+  explicit StreamScope(cudaStream_t s) : saved(ctx().stream) { ctx().stream = s; }
+  ~StreamScope() { ctx().stream = saved; }
+};
+
+// front half of one batch: transform + geometry + tables, tile bitmaps, boxes, per-tile lists
+int batch_front(vt_fit_ctx *f, PoseBatch &pb, const float com[3], const PrepPose *d_prep, int n) {
+  int rc = batch_prepare(f->as, pb, n, d_prep, com, 0, &f->target->grid);
+  if (!rc) rc = batch_splat_front(f->as, pb, n);
   return rc;
+}
+
+// back half: accumulate the density grids, score them against the target
+int batch_back(vt_fit_ctx *f, PoseBatch &pb, int n, float *d_cc) {
+  int rc = batch_splat_back(f->as, pb, n);
+  if (!rc) rc = batch_cc(pb, n, f->target, f->threshold, d_cc, nullptr);
+  return rc;
+}
+
+// run the pipeline for poses already prepared on the device (d_prep[nposes]); everything is
+// enqueued without a host round trip
+int eval_prepared(vt_fit_ctx *f, const float com[3], const PrepPose *d_prep, long nposes, float *d_cc) {
+  Ctx &c = ctx();
+  const long nb = (nposes + f->B - 1) / f->B;
+  auto count = [&](long i) { return (int)std::min<long>(f->B, nposes - i * f->B); };
+  if (f->nslots < 2 || nb < 2) {
+    for (long i = 0; i < nb; ++i) {
+      int rc = batch_front(f, f->pb[0], com, d_prep + i * f->B, count(i));
+      if (!rc) rc = batch_back(f, f->pb[0], count(i), d_cc + i * f->B);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  VT_CUDA(cudaEventRecord(f->ev_start, c.stream));       // the second stream starts after everything queued so far
+  VT_CUDA(cudaStreamWaitEvent(f->aux, f->ev_start, 0));
+  auto front = [&](long i) -> int {
+    const int slot = (int)(i & 1);
+    if (i >= 2) VT_CUDA(cudaStreamWaitEvent(f->aux, f->ev_back[slot], 0));   // the slot's previous batch has been scored
+    int rc;
+    {
+      StreamScope scope(f->aux);
+      rc = batch_front(f, f->pb[slot], com, d_prep + i * f->B, count(i));
+    }
+    if (rc) return rc;
+    VT_CUDA(cudaEventRecord(f->ev_front[slot], f->aux));
+    return 0;
+  };
+  int rc = front(0);
+  for (long i = 0; i < nb && !rc; ++i) {
+    const int slot = (int)(i & 1);
+    if (i + 1 < nb) rc = front(i + 1);
+    if (rc) break;
+    VT_CUDA(cudaStreamWaitEvent(c.stream, f->ev_front[slot], 0));
+    rc = batch_back(f, f->pb[slot], count(i), d_cc + i * f->B);
+    if (rc) break;
+    VT_CUDA(cudaEventRecord(f->ev_back[slot], c.stream));
+  }
+  return rc;
+}
+
+int reset_overflow(vt_fit_ctx *f) {
+  for (int k = 0; k < f->nslots; ++k)
+    if (f->pb[k].use_lists) VT_CUDA(cudaMemsetAsync(f->pb[k].d_totals + 2, 0, sizeof(int), ctx().stream));
+  return 0;
+}
+
+// 1 in *flag if a tile list of either workspace overflowed since reset_overflow (synchronises)
+int any_overflow(vt_fit_ctx *f, int *flag) {
+  *flag = 0;
+  for (int k = 0; k < f->nslots; ++k)
+    if (f->pb[k].use_lists) {
+      int ovf = 0;
+      int rc = batch_lists_overflowed(f->pb[k], &ovf);
+      if (rc) return rc;
+      *flag |= ovf;
+    }
+  return 0;
 }
 
 int cuda_table_eval(void *user, const float *origin_pos, const float com[3], int stride, int max_rot, int first,
@@ -219,15 +317,24 @@ int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_ma
   f->B = env ? atoi(env) : 128;
   if (f->B < 1) f->B = 1;
   if (f->B > 1024) f->B = 1024;
-  rc = batch_create(f->as, &target->grid, f->B, f->pb);
-  if (!rc) {
-    const float com0[3] = {0.f, 0.f, 0.f};
-    rc = batch_prepare(f->as, f->pb, 1, nullptr, com0, 1, &target->grid);
-    if (!rc) rc = batch_calibrate_lists(f->as, f->pb);
+  const char *ov = getenv("VOLTOOL_FIT_OVERLAP");
+  f->nslots = (ov && atoi(ov) == 0) ? 1 : 2;
+  for (int k = 0; k < f->nslots && !rc; ++k) {
+    rc = batch_create(f->as, &target->grid, f->B, f->pb[k]);
+    if (!rc) {
+      const float com0[3] = {0.f, 0.f, 0.f};
+      rc = batch_prepare(f->as, f->pb[k], 1, nullptr, com0, 1, &target->grid);
+      if (!rc) rc = batch_calibrate_lists(f->as, f->pb[k]);
+    }
   }
-  if (!rc) {
-    cudaError_t e = cudaMallocHost((void **)&f->h_prep, sizeof(PrepPose) * f->B);
-    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+  if (!rc && f->nslots > 1) {
+    cudaError_t e = cudaStreamCreateWithFlags(&f->aux, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_start, cudaEventDisableTiming);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+      e = cudaEventCreateWithFlags(&f->ev_front[k], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_back[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) rc = cuda_fail(e, "fit streams", __FILE__, __LINE__);
   }
   if (rc) { vt_fit_destroy(f); return rc; }
   *out = f;
@@ -236,10 +343,18 @@ int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_ma
 
 int vt_fit_destroy(vt_fit_ctx *f) {
   if (!f) return 0;
+  if (f->aux) cudaStreamSynchronize(f->aux);
   cudaStreamSynchronize(ctx().stream);
-  batch_destroy(f->pb);
+  for (int k = 0; k < 2; ++k) {
+    batch_destroy(f->pb[k]);
+    if (f->ev_front[k]) cudaEventDestroy(f->ev_front[k]);
+    if (f->ev_back[k]) cudaEventDestroy(f->ev_back[k]);
+  }
+  if (f->ev_start) cudaEventDestroy(f->ev_start);
+  if (f->aux) cudaStreamDestroy(f->aux);
   atomset_destroy(f->as);
   dev_free(f->d_cc);
+  dev_free(f->d_prep);
   if (f->h_prep) cudaFreeHost(f->h_prep);
   delete f;
   return 0;
@@ -254,57 +369,51 @@ int vt_fit_eval_poses(vt_fit_ctx *f, const float com[3], const vt_pose *poses, l
   VT_REQUIRE_CTX();
   if (nposes <= 0) return 0;
   int rc = ensure_cc_buffer(f, nposes);
+  if (!rc) rc = ensure_prep_buffers(f, nposes, true);
   if (rc) return rc;
   Ctx &c = ctx();
-  if (f->pb.use_lists) VT_CUDA(cudaMemsetAsync(f->pb.d_totals + 2, 0, sizeof(int), c.stream));
-  for (long p0 = 0; p0 < nposes; p0 += f->B) {
-    const int n = (int)std::min<long>(f->B, nposes - p0);
-    // the pinned staging buffer is reused: wait for the previous batch's upload to be consumed
-    VT_CUDA(cudaStreamSynchronize(c.stream));
-    for (int i = 0; i < n; ++i) {
-      const vt_pose &q = poses[p0 + i];
-      for (int k = 0; k < 3; ++k) {
-        euler_cs((double)q.rot_deg[k], f->h_prep[i].c[k], f->h_prep[i].s[k]);
-        f->h_prep[i].shift[k] = q.shift[k];
-      }
+  VT_CUDA(cudaStreamSynchronize(c.stream));   // the pinned staging buffer may still feed an earlier call's upload
+  for (long i = 0; i < nposes; ++i) {
+    const vt_pose &q = poses[i];
+    for (int k = 0; k < 3; ++k) {
+      euler_cs((double)q.rot_deg[k], f->h_prep[i].c[k], f->h_prep[i].s[k]);
+      f->h_prep[i].shift[k] = q.shift[k];
     }
-    VT_CUDA(cudaMemcpyAsync(f->pb.d_prep, f->h_prep, sizeof(PrepPose) * n, cudaMemcpyHostToDevice, c.stream));
-    rc = eval_prepared(f, com, f->pb.d_prep, n, f->d_cc + p0);
-    if (rc) return rc;
   }
+  VT_CUDA(cudaMemcpyAsync(f->d_prep, f->h_prep, sizeof(PrepPose) * (size_t)nposes, cudaMemcpyHostToDevice, c.stream));
+  rc = reset_overflow(f);
+  if (!rc) rc = eval_prepared(f, com, f->d_prep, nposes, f->d_cc);
+  if (rc) return rc;
   VT_CUDA(cudaMemcpyAsync(cc_out, f->d_cc, sizeof(float) * (size_t)nposes, cudaMemcpyDeviceToHost, c.stream));
   VT_CUDA(cudaStreamSynchronize(c.stream));
-  if (f->pb.use_lists) {
-    int ovf = 0;
-    rc = batch_lists_overflowed(f->pb, &ovf);
-    if (rc) return rc;
-    if (ovf) {  // a tile list was too small: nothing is truncated silently, redo with the cooperative kernel
-      f->pb.use_lists = false;
-      return vt_fit_eval_poses(f, com, poses, nposes, cc_out);
-    }
+  int ovf = 0;
+  rc = any_overflow(f, &ovf);
+  if (rc) return rc;
+  if (ovf) {  // a tile list was too small: nothing is truncated silently, redo with the cooperative kernel
+    for (int k = 0; k < 2; ++k) f->pb[k].use_lists = false;
+    return vt_fit_eval_poses(f, com, poses, nposes, cc_out);
   }
   return 0;
 }
 
 int vt_fit_eval_poses_device(vt_fit_ctx *f, const float com[3], const vt_pose *d_poses, long nposes, float *d_cc) {
   VT_REQUIRE_CTX();
+  if (nposes <= 0) return 0;
   Ctx &c = ctx();
-  if (f->pb.use_lists) VT_CUDA(cudaMemsetAsync(f->pb.d_totals + 2, 0, sizeof(int), c.stream));
-  for (long p0 = 0; p0 < nposes; p0 += f->B) {
-    const int n = (int)std::min<long>(f->B, nposes - p0);
-    prep_from_pose_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(d_poses + p0, n, f->pb.d_prep);
-    VT_LAUNCHED();
-    int rc = eval_prepared(f, com, f->pb.d_prep, n, d_cc + p0);
-    if (rc) return rc;
-  }
-  if (f->pb.use_lists) {  // one 4-byte readback per call: a truncated tile list must never go unnoticed
-    int ovf = 0;
-    int rc = batch_lists_overflowed(f->pb, &ovf);
-    if (rc) return rc;
-    if (ovf) {
-      f->pb.use_lists = false;
-      return vt_fit_eval_poses_device(f, com, d_poses, nposes, d_cc);
-    }
+  int rc = ensure_prep_buffers(f, nposes, false);
+  if (!rc) rc = reset_overflow(f);
+  if (rc) return rc;
+  prep_from_pose_kernel<<<(unsigned int)((nposes + 127) / 128), 128, 0, c.stream>>>(d_poses, (int)nposes, f->d_prep);
+  VT_LAUNCHED();
+  rc = eval_prepared(f, com, f->d_prep, nposes, d_cc);
+  if (rc) return rc;
+  // one 4-byte readback per workspace and call: a truncated tile list must never go unnoticed
+  int ovf = 0;
+  rc = any_overflow(f, &ovf);
+  if (rc) return rc;
+  if (ovf) {
+    for (int k = 0; k < 2; ++k) f->pb[k].use_lists = false;
+    return vt_fit_eval_poses_device(f, com, d_poses, nposes, d_cc);
   }
   return 0;
 }

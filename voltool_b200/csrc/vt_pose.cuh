@@ -101,6 +101,11 @@ int batch_splat(const AtomSet &as, PoseBatch &pb, int npose);
 // batch_prepare first); leaves the cooperative kernel in place when it does not apply
 int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb);
 int batch_splat_lists(const AtomSet &as, PoseBatch &pb, int npose);
+// the splat in two halves, so that a caller can run the list building of the next batch on a second
+// stream while this batch accumulates: front = tile bitmaps (+ boxes and per-tile lists), back = the
+// accumulation kernel.  batch_splat == front then back.
+int batch_splat_front(const AtomSet &as, PoseBatch &pb, int npose);
+int batch_splat_back(const AtomSet &as, PoseBatch &pb, int npose);
 int batch_bin(const AtomSet &as, PoseBatch &pb, int npose);
 // 1 if a tile list overflowed since the last reset (synchronises)
 int batch_lists_overflowed(PoseBatch &pb, int *flag);

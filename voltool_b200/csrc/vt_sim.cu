@@ -701,12 +701,23 @@ int batch_bin(const AtomSet &as, PoseBatch &pb, int npose) {
   return 0;
 }
 
-int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
+int batch_lists_front(const AtomSet &as, PoseBatch &pb, int npose);
+int batch_lists_back(const AtomSet &as, PoseBatch &pb, int npose);
+
+static bool lists_on(const PoseBatch &pb) { return pb.use_lists && !getenv("VOLTOOL_SPLAT_COOP"); }
+
+int batch_splat_front(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
-  Ctx &c = ctx();
   int rc = batch_bin(as, pb, npose);
   if (rc) return rc;
-  if (pb.use_lists && !getenv("VOLTOOL_SPLAT_COOP")) return batch_splat_lists(as, pb, npose);
+  if (lists_on(pb)) return batch_lists_front(as, pb, npose);
+  return 0;
+}
+
+int batch_splat_back(const AtomSet &as, PoseBatch &pb, int npose) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  if (lists_on(pb)) return batch_lists_back(as, pb, npose);
   const int nwords = (as.ngroups + 31) / 32;
   const int grid = c.sm_count * (kSplatWarps == 4 ? 6 : 3) * 4;  // persistent: resident CTAs per SM x 4 rounds
   prof_begin(PK_SPLAT);
@@ -721,6 +732,12 @@ int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
   prof_end(PK_SPLAT);
   VT_LAUNCHED();
   return 0;
+}
+
+int batch_splat(const AtomSet &as, PoseBatch &pb, int npose) {
+  int rc = batch_splat_front(as, pb, npose);
+  if (!rc) rc = batch_splat_back(as, pb, npose);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------ batched cc

@@ -327,7 +327,7 @@ int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb) {
 }
 
 // returns 0 on launch; the overflow flag (d_totals[2]) must be checked by the caller after a sync
-int batch_splat_lists(const AtomSet &as, PoseBatch &pb, int npose) {
+int batch_lists_front(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
   const int nwords = (as.ngroups + 31) / 32;
@@ -340,6 +340,12 @@ int batch_splat_lists(const AtomSet &as, PoseBatch &pb, int npose) {
                                                       pb.d_boxes, pb.d_tlist, pb.d_tcount, pb.cap_t, pb.d_totals + 2);
   prof_end(PK_SETUP);
   VT_LAUNCHED();
+  return 0;
+}
+
+int batch_lists_back(const AtomSet &as, PoseBatch &pb, int npose) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
   prof_begin(PK_SPLAT);
   splat_list_kernel<<<c.sm_count * 6 * 4, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, pb.d_tpos, as.d_const,
                                                               pb.d_boxes, pb.d_tlist, pb.d_tcount, pb.cap_t, pb.tiles_cap,
@@ -347,6 +353,12 @@ int batch_splat_lists(const AtomSet &as, PoseBatch &pb, int npose) {
   prof_end(PK_SPLAT);
   VT_LAUNCHED();
   return 0;
+}
+
+int batch_splat_lists(const AtomSet &as, PoseBatch &pb, int npose) {
+  int rc = batch_lists_front(as, pb, npose);
+  if (!rc) rc = batch_lists_back(as, pb, npose);
+  return rc;
 }
 
 }  // namespace vt
