@@ -269,8 +269,9 @@ int k_cc(const vt_map *A, const vt_map *B, double thr, double sums[5], long *n) 
     *n = 0;
     return 0;
   }
+  // (the separable kernels address source rows with 32-bit byte offsets inside a plane)
   const bool sep = axis_aligned_out(dC) && diagonal_inverse(dA.inv) && diagonal_inverse(dB.inv) && finite_geom(dC) &&
-                   !getenv("VOLTOOL_FORCE_GENERIC");
+                   (long)dA.nx * dA.ny < (1L << 30) && (long)dB.nx * dB.ny < (1L << 30) && !getenv("VOLTOOL_FORCE_GENERIC");
   if (sep) {
     SepTables T;
     int rc = upload_tables(dC, dA, dB, T);

@@ -305,6 +305,10 @@ int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_ma
                   vt_fit_ctx **out) {
   VT_REQUIRE_CTX();
   if (!pos || !radii || !target || natoms <= 0) { set_error("vt_fit_create: bad arguments"); return 1; }
+  if ((long)target->grid.xsize * target->grid.ysize >= (1L << 30)) {
+    set_error("vt_fit_create: target planes of 2^30 voxels or more are not supported");
+    return 1;
+  }
   vt_fit_ctx *f = new vt_fit_ctx();
   f->target = target;
   f->resolution = resolution;
