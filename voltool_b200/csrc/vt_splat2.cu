@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128) gather_kernel(const PoseGeom *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------ accumulate
-constexpr int kRec2 = 24;  // Ex[8] | dy^2[8] | dz^2[4] | arinv, radlim^2, pad, pad
+constexpr int kRec2 = 28;  // Ex[8] | dy^2[8] | dz^2[4] | arinv, radlim^2, pad x 6 (stride 28: the 16-byte staging stores of 8 lanes cover all 32 banks)
 
 __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__restrict__ geo,
                                                             const int *__restrict__ totals, int npose, int natoms,
