@@ -515,7 +515,7 @@ def cfg5_leg(vt, natoms, edge):
     dt = time.perf_counter() - t0
     res["refine"] = {"poses": n_eval, "seconds": dt, "poses_per_s": n_eval / dt, "best_deg": best.tolist(),
                      "planted_deg": list(planted), "best_cc": best_cc,
-                     "note": "Euler angles about x, y, z compose, so the winner matches the planted triple only approximately"}
+                     "note": "two stages of 7^3 Euler triples (4 deg, then 1 deg about the winner); the planted triple lies on that lattice"}
     ctx.close()
     return res
 
