@@ -113,6 +113,14 @@ int vt_dx_write(const char *path, const vt_grid *g, const float *data, const cha
 int vt_dx_read(const char *path, vt_grid *g, float **data);
 int vt_map_write_dx(const vt_map *m, const char *path, const char *name);  /* `-o <file>` of sim/cc, TclMDFF.C:159 */
 int vt_map_read_dx(const char *path, vt_map **out);                         /* `-i <input map>`, TclMDFF.C:176 */
+/* MRC2014 / CCP4 maps (what VMD's ccp4plugin hands to `mol new`; the plugin is not in the snapshot, the
+ * mapping onto VolumetricData geometry is restated in vt_io.cpp).  Read: modes 0/1/2/6, any axis order,
+ * either byte order, orthogonal cells.  Write: mode 2.  vt_mrc_* are host only; vt_mrc_read mallocs *data
+ * (release: vt_free_host). */
+int vt_mrc_write(const char *path, const vt_grid *g, const float *data);
+int vt_mrc_read(const char *path, vt_grid *g, float **data);
+int vt_map_write_mrc(const vt_map *m, const char *path);
+int vt_map_read_mrc(const char *path, vt_map **out);
 
 /* ---------------------------------------------------------------- resizing ops (replace data) */
 int vt_pad(vt_map *m, int padxm, int padxp, int padym, int padyp, int padzm, int padzp); /* ::pad :542-609; trim = pad(-t) TclVoltool.C:1185 */

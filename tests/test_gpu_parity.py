@@ -25,6 +25,12 @@ def same_grid(g1, g2):
     return t1[4] == t2[4] and all(np.array_equal(np.array(a), np.array(b), equal_nan=True) for a, b in zip(t1[:4], t2[:4]))
 
 
+def same_grid_tuple(g1, g2, tol=1e-5):
+    """geometry after a trip through MRC's float header words"""
+    t1, t2 = g1.astuple(), g2.astuple()
+    return t1[4] == t2[4] and all(np.allclose(np.array(a), np.array(b), rtol=tol, atol=tol) for a, b in zip(t1[:4], t2[:4]))
+
+
 def rng_map(seed, n):
     return np.random.default_rng(seed).random(n, dtype=np.float32)
 
@@ -527,3 +533,13 @@ def test_cli_commands_match_api(tmp_path, capsys):
     assert cli.main(["cc", "-atoms", pt, "-res", "5", "-i", ps]) == 0
     assert abs(float(capsys.readouterr().out) - 1.0) < 1e-6
     assert cli.main(["smooth", "-i", pa]) == 1          # -sigma missing: usage error, nothing written
+    # MRC / CCP4 maps through the same commands (chosen by extension)
+    pm, pom = str(tmp_path / "a.mrc"), str(tmp_path / "o.ccp4")
+    vt.VolMap(g, a).write_mrc(pm)
+    M = vt.VolMap.read_mrc(pm)
+    assert np.array_equal(bits(M.data), bits(a)) and same_grid_tuple(M.grid, g)
+    assert cli.main(["downsample", "-i", pm, "-o", pom]) == 0
+    D = vt.VolMap(g, a).downsample()
+    g3, d3 = vt.read_mrc(pom)
+    assert (g3.xsize, g3.ysize, g3.zsize) == (D.grid.xsize, D.grid.ysize, D.grid.zsize)
+    assert np.array_equal(bits(d3), bits(D.data))

@@ -264,3 +264,71 @@ def test_cli_option_parsing():
     with pytest.raises(cli.UsageError):
         cli.parse("range", ["-minmax", "1"])
     assert cli.main([]) == 1 and cli.main(["help"]) == 0
+
+
+# ------------------------------------------------------------------------------------------ MRC / CCP4 files (host only)
+def _mrc_header(nc, nr, ns, mode, mapcrs=(1, 2, 3), start=(0, 0, 0), m=None, cell=None, origin=(0, 0, 0), endian="<",
+                nsymbt=0):
+    import struct
+    m = m or (nc, nr, ns)
+    cell = cell or tuple(float(v) for v in m)
+    words = [0] * 256
+    h = bytearray(1024)
+    struct.pack_into(endian + "10i", h, 0, nc, nr, ns, mode, *start, *m)
+    struct.pack_into(endian + "6f", h, 40, *cell, 90.0, 90.0, 90.0)
+    struct.pack_into(endian + "3i", h, 64, *mapcrs)
+    struct.pack_into(endian + "i", h, 92, nsymbt)
+    struct.pack_into(endian + "3f", h, 196, *origin)
+    h[208:212] = b"MAP "
+    h[212:216] = bytes([0x44, 0x44, 0, 0]) if endian == "<" else bytes([0x11, 0x11, 0, 0])
+    return bytes(h)
+
+
+def test_mrc_round_trip(tmp_path):
+    g = vt.Grid.make((1.5, -2.25, 10.0), (7, 5, 6), (1.0, 1.5, 0.5))
+    a = np.random.default_rng(5).standard_normal(g.n).astype(np.float32)
+    path = str(tmp_path / "m.mrc")
+    vt.write_mrc(path, g, a)
+    g2, b = vt.read_mrc(path)
+    assert (g2.xsize, g2.ysize, g2.zsize) == (7, 5, 6)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.allclose(np.array(g2.origin), np.array(g.origin)) and np.allclose(np.array(g2.xaxis), np.array(g.xaxis))
+    assert np.allclose(np.array(g2.yaxis), np.array(g.yaxis)) and np.allclose(np.array(g2.zaxis), np.array(g.zaxis), rtol=1e-6)
+    raw = open(path, "rb").read()
+    assert len(raw) == 1024 + 4 * g.n and raw[208:212] == b"MAP "
+
+
+def test_mrc_modes_axis_order_and_byte_order(tmp_path):
+    # mode 1 (int16), columns = Z, rows = Y, sections = X, big-endian, with an extended header and NSTART
+    nc, nr, ns = 4, 3, 5                      # = nz, ny, nx
+    vals = np.arange(nc * nr * ns, dtype=np.int16).reshape(ns, nr, nc) - 17
+    hdr = _mrc_header(nc, nr, ns, 1, mapcrs=(3, 2, 1), start=(2, 0, -1), m=(8, 6, 10), cell=(16.0, 6.0, 5.0),
+                      origin=(0, 0, 0), endian=">", nsymbt=80)
+    path = str(tmp_path / "be.map")
+    with open(path, "wb") as f:
+        f.write(hdr + b"\0" * 80 + vals.astype(">i2").tobytes())
+    g, d = vt.read_mrc(path)
+    assert (g.xsize, g.ysize, g.zsize) == (ns, nr, nc)
+    want = np.transpose(vals.astype(np.float32), (2, 1, 0))   # file [x][y][z] -> memory [z][y][x]
+    assert np.array_equal(d.reshape(nc, nr, ns), want)
+    # voxel = CELLA / M per axis: x 16/8 = 2, y 6/6 = 1, z 5/10 = 0.5; NSTART belongs to the file axes (c=Z, r=Y, s=X)
+    assert np.allclose(np.array(g.origin), [-1 * 2.0, 0.0, 2 * 0.5])
+    assert np.allclose([g.xaxis[0], g.yaxis[1], g.zaxis[2]], [2.0 * (ns - 1), 1.0 * (nr - 1), 0.5 * (nc - 1)])
+    # mode 0 (int8) and mode 6 (uint16), little-endian, words 50-52 origin
+    for mode, dt in ((0, "i1"), (6, "<u2"), (2, "<f4")):
+        v = (np.arange(24) * 9 % 200).astype(dt).reshape(2, 3, 4)
+        p2 = str(tmp_path / f"m{mode}.mrc")
+        with open(p2, "wb") as f:
+            f.write(_mrc_header(4, 3, 2, mode, origin=(5.0, 6.0, 7.0)) + v.tobytes())
+        g2, d2 = vt.read_mrc(p2)
+        assert np.array_equal(d2, v.astype(np.float32).reshape(-1)) and tuple(g2.origin) == (5.0, 6.0, 7.0)
+    # errors: truncated data, unsupported mode, non-orthogonal cell
+    bad = str(tmp_path / "bad.mrc")
+    with open(bad, "wb") as f:
+        f.write(_mrc_header(4, 3, 2, 2) + b"\0" * 10)
+    with pytest.raises(vt.VoltoolGpuError):
+        vt.read_mrc(bad)
+    with open(bad, "wb") as f:
+        f.write(_mrc_header(4, 3, 2, 4) + b"\0" * 400)
+    with pytest.raises(vt.VoltoolGpuError):
+        vt.read_mrc(bad)

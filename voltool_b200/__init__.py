@@ -13,10 +13,10 @@ from .api import (Grid, Cache, Pose, FitResult, VolMap, VoltoolGpuError, lib, li
                   launch_count, device_props, cc_threaded, add, subtract, multiply, average, binary, sim, sim_policy,
                   calc_cc, sim_cc, fit, FitContext, rotate_replay, pose_apply, measure_center, fit_schedule,
                   init_from_intersection, init_from_union, profile_enable, profile_reset, profile_get, write_dx,
-                  read_dx)
+                  read_dx, write_mrc, read_mrc)
 
 __all__ = ["Grid", "Cache", "Pose", "FitResult", "VolMap", "VoltoolGpuError", "lib", "lib_path", "init", "shutdown",
            "sync", "launch_count", "device_props", "cc_threaded", "add", "subtract", "multiply", "average", "binary",
            "sim", "sim_policy", "calc_cc", "sim_cc", "fit", "FitContext", "rotate_replay", "pose_apply",
            "measure_center", "fit_schedule", "init_from_intersection", "init_from_union", "profile_enable",
-           "profile_reset", "profile_get", "write_dx", "read_dx"]
+           "profile_reset", "profile_get", "write_dx", "read_dx", "write_mrc", "read_mrc"]

@@ -149,6 +149,10 @@ def lib():
     L.vt_dx_read.argtypes = [C.c_char_p, G, C.POINTER(c_float_p)]
     L.vt_map_write_dx.argtypes = [M, C.c_char_p, C.c_char_p]
     L.vt_map_read_dx.argtypes = [C.c_char_p, C.POINTER(M)]
+    L.vt_mrc_write.argtypes = [C.c_char_p, G, C.c_void_p]
+    L.vt_mrc_read.argtypes = [C.c_char_p, G, C.POINTER(c_float_p)]
+    L.vt_map_write_mrc.argtypes = [M, C.c_char_p]
+    L.vt_map_read_mrc.argtypes = [C.c_char_p, C.POINTER(M)]
     L.vt_init_from_intersection.argtypes = [G, G, G]
     L.vt_init_from_union.argtypes = [G, G, G]
     L.vt_sim_policy.argtypes = [C.c_double, C.c_double, c_float_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -326,6 +330,28 @@ class VolMap:
         _check(lib().vt_map_read_dx(os.fsencode(path), C.byref(h)), "vt_map_read_dx")
         return cls(_handle=h)
 
+    def write_mrc(self, path):
+        _need()
+        _check(lib().vt_map_write_mrc(self.h, os.fsencode(path)), "vt_map_write_mrc")
+
+    @classmethod
+    def read_mrc(cls, path):
+        _need()
+        h = C.c_void_p()
+        _check(lib().vt_map_read_mrc(os.fsencode(path), C.byref(h)), "vt_map_read_mrc")
+        return cls(_handle=h)
+
+    @classmethod
+    def read_file(cls, path):
+        """by extension: .mrc / .map / .ccp4 -> MRC, anything else -> OpenDX"""
+        return cls.read_mrc(path) if is_mrc_path(path) else cls.read_dx(path)
+
+    def write_file(self, path, name="density"):
+        if is_mrc_path(path):
+            self.write_mrc(path)
+        else:
+            self.write_dx(path, name)
+
     def clamp(self, lo, hi):
         _check(lib().vt_clamp(self.h, lo, hi), "vt_clamp"); return self
 
@@ -412,6 +438,30 @@ def read_dx(path):
     g = Grid()
     p = c_float_p()
     _check(lib().vt_dx_read(os.fsencode(path), C.byref(g), C.byref(p)), "vt_dx_read")
+    try:
+        out = np.ctypeslib.as_array(p, shape=(max(g.n, 1),))[:g.n].copy()
+    finally:
+        lib().vt_free_host(p)
+    return g, out
+
+
+def is_mrc_path(path):
+    return os.fspath(path).lower().endswith((".mrc", ".map", ".ccp4"))
+
+
+def write_mrc(path, grid, data):
+    """host arrays -> MRC2014 file, mode 2 (no GPU needed)"""
+    d = f32(data)
+    if d.size != grid.n:
+        raise ValueError("data size does not match the grid")
+    _check(lib().vt_mrc_write(os.fsencode(path), C.byref(grid), _vp(d)), "vt_mrc_write")
+
+
+def read_mrc(path):
+    """MRC / CCP4 file -> (Grid, float32 array in map order: x fastest); no GPU needed"""
+    g = Grid()
+    p = c_float_p()
+    _check(lib().vt_mrc_read(os.fsencode(path), C.byref(g), C.byref(p)), "vt_mrc_read")
     try:
         out = np.ctypeslib.as_array(p, shape=(max(g.n, 1),))[:g.n].copy()
     finally:

@@ -120,11 +120,11 @@ def run(cmd, o, pos):
         return o[k]
 
     def load(k="-i"):
-        return vt.VolMap.read_dx(need(k))
+        return vt.VolMap.read_file(need(k))      # .mrc / .map / .ccp4 or OpenDX
 
     def save(m, k="-o"):
         if k in o:
-            m.write_dx(o[k])
+            m.write_file(o[k])
 
     one_map = {"smooth", "smult", "sadd", "range", "clamp", "binmask", "pot", "sigma", "downsample", "supersample",
                "trim", "crop", "moveto", "move"}
@@ -211,7 +211,7 @@ def run(cmd, o, pos):
             r = vt.sim_cc(apos, radii, res, target, thr, gs, want_synth=want)
             if want:
                 cc, synth = r
-                synth.write_dx(o["-savesynthmap"])
+                synth.write_file(o["-savesynthmap"])
             else:
                 cc = r
             print("%.9g" % cc)
