@@ -162,9 +162,21 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL_DEBUG=VERSION (set on the GPU boxes) prints to stdout by default: keep stdout to the one JSON line
+        # NCCL prints its version banner with a plain printf when the first communicator comes up: send
+        # stdout to stderr while that happens, so that stdout carries only the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     vt.init(local)
     props = vt.device_props()
     stream = torch.cuda.ExternalStream(vt.lib().vt_stream(), device=torch.device("cuda", local))
