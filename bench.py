@@ -342,6 +342,16 @@ def run_ours(args):
             out["ops"] = extra_ops(vt, peaks, args)
             if args.cfg4_map > 0:
                 out["cfg4"] = cfg4_legs(vt, peaks, args.cfg4_map)
+                # the HBM-bound kernel of the path in the same shape as `roofline` (which describes the
+                # FP32/shared-memory-bound splat): correlate of two resident maps, 8 B/voxel algorithmic
+                c4 = out["cfg4"]["correlate"]
+                nvox = float(args.cfg4_map) ** 3
+                out["roofline_hbm"] = {"kernel": "cc_identity_kernel", "bound": "hbm", "achieved": c4["GB/s"],
+                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": c4["frac_hbm"],
+                                       "traffic": 8.590082e9 + 3.345e6 if args.cfg4_map == 1024 else None,
+                                       "traffic_source": "profiles/r1e_cc_identity_1024_summary.txt (dram read + write per launch); "
+                                                         f"algorithmic {8.0 * nvox:.4g} B",
+                                       "peak_source": f"{peaks['source']} MEASURED_PEAKS hbm_gbs", "ms_per_launch": c4["ms"]}
             if args.cfg5_atoms > 0:
                 out["cfg5"] = cfg5_leg(vt, args.cfg5_atoms, args.cfg5_edge)
     print(json.dumps(out))
