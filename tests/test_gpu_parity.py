@@ -380,9 +380,13 @@ def test_supersample_known_answers():
     assert np.all(const == 2.5)
 
 
+@pytest.mark.parametrize("mode", ["", "yz"])
 @pytest.mark.parametrize("sigma", [0.6, 1.5, 2.0])
-def test_blur_bit_exact(oracle, sigma):
-    for size in [(20, 17, 15), (64, 9, 33), (5, 4, 3)]:
+def test_blur_bit_exact(oracle, sigma, mode, monkeypatch):
+    """default path and the x | y+z form (z pass as a register scatter), incl. maps thinner than the radius"""
+    if mode:
+        monkeypatch.setenv("VOLTOOL_BLUR_MODE", mode)
+    for size in [(20, 17, 15), (64, 9, 33), (5, 4, 3), (36, 35, 70), (8, 3, 2), (132, 40, 5)]:
         g = OGrid.make((0, 0, 0), size, 1.0)
         d = rng_map(9, g.n)
         m = vt.VolMap(G(g), d).gaussian_blur(sigma)

@@ -10,6 +10,7 @@
 #include <climits>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "vt_device.cuh"
 
@@ -342,6 +343,176 @@ __global__ void __launch_bounds__(256) blur_z4_kernel(const float *__restrict__ 
     if (a0 + s < nz) dst[(long)(a0 + s) * quads] = acc[s];
 }
 
+// ---- y and z passes in one kernel --------------------------------------------------------------------
+// A thread owns two adjacent columns (one packed pair) and two adjacent rows, and marches a chunk of z.
+// Per input plane it reads the 2 + 2R x-blurred rows of its y window (8-byte loads; the rows shared with
+// neighbouring threads come from L1), forms its two y-blurred pairs (taps in order, FFMA2), and scatters
+// them into 2R+1 pending z outputs per pair that live in registers: input plane zin is tap k of output
+// zin + R - k, so every output receives its taps in the order k = 0 .. 2R, exactly the chain of the
+// gather form (acc = fma(w[k], v[clamp(z + k - R)], acc) from 0).  The output whose last tap just
+// arrived is stored.  Accumulator slots rotate with zin; the rotation is resolved at compile time by
+// dispatching on zin mod (2R+1).  Edge planes are replicated by feeding the clamped plane's values for
+// the virtual planes zin < 0 and zin >= nz.  No shared memory, no barrier; HBM traffic is the
+// intermediate once plus the output once.
+template <int R, int S>
+__device__ __forceinline__ void blur_z_scatter(f32x2 (&acc)[2][2 * R + 1], const f32x2 (&v)[2], const f32x2 (&w2)[2 * R + 1],
+                                               bool emit, float2 *__restrict__ o0, float2 *__restrict__ o1, bool ok0, bool ok1) {
+  constexpr int NT = 2 * R + 1;
+#pragma unroll
+  for (int k = 0; k < NT; ++k) {
+    constexpr int dummy = 0; (void)dummy;
+    const int slot = (S + R - k + 2 * NT) % NT;   // slot of output zin + R - k, with slot(z) = z mod NT and S = zin mod NT
+#pragma unroll
+    for (int c = 0; c < 2; ++c) acc[c][slot] = fma2(w2[k], v[c], k == 0 ? pack2(0.0f, 0.0f) : acc[c][slot]);
+  }
+  if (emit) {   // output zin - R: its last tap (k = 2R) was just added
+    constexpr int slot = (S - R + 2 * NT) % NT;
+    float a, b;
+    if (ok0) { unpack2(acc[0][slot], a, b); __stcs(o0, make_float2(a, b)); }
+    if (ok1) { unpack2(acc[1][slot], a, b); __stcs(o1, make_float2(a, b)); }
+  }
+}
+
+// one real branch per step (a switch, i.e. a jump table): an if-chain gets if-converted into predicated
+// copies, which issues two scatter bodies per step
+template <int R>
+__device__ __forceinline__ void blur_z_dispatch(int s, f32x2 (&acc)[2][2 * R + 1], const f32x2 (&v)[2],
+                                                const f32x2 (&w2)[2 * R + 1], bool emit, float2 *__restrict__ o0,
+                                                float2 *__restrict__ o1, bool ok0, bool ok1) {
+  constexpr int NT = 2 * R + 1;
+#define VT_ZCASE(S) case S: if constexpr (S < NT) blur_z_scatter<R, (S < NT ? S : 0)>(acc, v, w2, emit, o0, o1, ok0, ok1); break;
+  switch (s) {
+    VT_ZCASE(0) VT_ZCASE(1) VT_ZCASE(2) VT_ZCASE(3) VT_ZCASE(4) VT_ZCASE(5) VT_ZCASE(6) VT_ZCASE(7) VT_ZCASE(8)
+    VT_ZCASE(9) VT_ZCASE(10) VT_ZCASE(11) VT_ZCASE(12) VT_ZCASE(13) VT_ZCASE(14) VT_ZCASE(15) VT_ZCASE(16)
+    default: break;
+  }
+#undef VT_ZCASE
+}
+
+constexpr int kYZx = 16, kYZy = 16;   // a CTA covers 16 column pairs x 16 row pairs = 32 x 32 voxels per plane
+constexpr int kYZStages = 4;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int R>
+__global__ void __launch_bounds__(kYZx * kYZy, 2) blur_yz_kernel(const float *__restrict__ in, float *__restrict__ out, int nx,
+                                                                 int ny, int nz, int xt, int yt, int zchunk) {
+  constexpr int NT = 2 * R + 1;
+  constexpr int ROWS = 2 * kYZy + 2 * R;       // staged rows per plane: the tile's rows + the y halo
+  constexpr int PITCH = 2 * kYZx;              // floats per staged row
+  constexpr int CHUNKS = ROWS * (PITCH / 4);   // 16-byte pieces per plane
+  constexpr int CIT = (CHUNKS + kYZx * kYZy - 1) / (kYZx * kYZy);
+  __shared__ __align__(16) float tile[kYZStages][ROWS * PITCH];
+  const int tid = threadIdx.x;
+  const long w = blockIdx.x;
+  const int tx = (int)(w % xt), ty = (int)((w / xt) % yt), zc = (int)(w / ((long)xt * yt));
+  const int lx = tid % kYZx, ly = tid / kYZx;
+  const int x0 = tx * PITCH, yb = ty * 2 * kYZy;   // tile origin
+  const int xp = (x0 >> 1) + lx;                   // column pair: voxels 2 xp, 2 xp + 1 (nx is a multiple of 4)
+  const int y0 = yb + 2 * ly;                      // rows y0, y0 + 1
+  const int zlo = zc * zchunk, zhi = min(nz, zlo + zchunk);
+  const bool ok0 = 2 * xp < nx && y0 < ny, ok1 = ok0 && y0 + 1 < ny;
+  const int nx2 = nx >> 1;
+  const long nxy = (long)nx * ny, nxy2 = (long)nx2 * ny;
+  // planes this chunk reads: clamp(zlo - R) .. clamp(zhi - 1 + R), staged in order, kYZStages - 1 ahead
+  const int pf = max(zlo - R, 0), pl = min(zhi - 1 + R, nz - 1);
+  const int nplanes = pl - pf + 1;
+  // this thread's 16-byte pieces of a plane tile: source address in plane pf (rows clamped to the map), slot
+  unsigned long long src[CIT];
+  int dsts[CIT];
+#pragma unroll
+  for (int i = 0; i < CIT; ++i) {
+    const int ch = tid + kYZx * kYZy * i;
+    const int row = ch / (PITCH / 4), q = ch - row * (PITCH / 4);
+    int y = yb - R + row;
+    y = y < 0 ? 0 : (y > ny - 1 ? ny - 1 : y);
+    const int x = x0 + 4 * q;
+    dsts[i] = (ch < CHUNKS && x < nx) ? row * PITCH + 4 * q : -1;
+    src[i] = (unsigned long long)(in + ((long)pf * nxy + (long)y * nx + min(x, nx - 4)));
+  }
+  const unsigned long long pstep = (unsigned long long)nxy * sizeof(float);
+  int staged = 0;
+  auto stage_plane = [&]() {
+    if (staged < nplanes) {
+      float *buf = tile[staged % kYZStages];
+#pragma unroll
+      for (int i = 0; i < CIT; ++i) {
+        if (dsts[i] >= 0) cp_async16(buf + dsts[i], reinterpret_cast<const void *>(src[i]));
+        src[i] += pstep;
+      }
+    }
+    cp_async_commit_group();
+    ++staged;
+  };
+  f32x2 acc[2][NT];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int k = 0; k < NT; ++k) acc[c][k] = pack2(0.0f, 0.0f);
+  f32x2 w2[NT];
+#pragma unroll
+  for (int k = 0; k < NT; ++k) w2[k] = pack2(c_taps[k], c_taps[k]);
+  f32x2 v[2] = {pack2(0.0f, 0.0f), pack2(0.0f, 0.0f)};
+  float2 *o0 = reinterpret_cast<float2 *>(out) + ((long)zlo * nxy2 + (long)y0 * nx2 + xp);
+#pragma unroll
+  for (int k = 0; k < kYZStages - 1; ++k) stage_plane();
+  int consumed = 0;
+  int s = ((zlo - R) % NT + NT) % NT;
+  const int wbase = (2 * ly) * PITCH + 2 * lx;   // first window row of this thread inside a staged tile
+  for (int zin = zlo - R; zin < zhi + R; ++zin) {
+    const int zp = zin < 0 ? 0 : (zin > nz - 1 ? nz - 1 : zin);
+    if (zp - pf == consumed) {                    // a new plane: uniform over the CTA
+      cp_async_wait_group<kYZStages - 2>();       // this thread's pieces of the plane have landed ...
+      __syncthreads();                            // ... and everybody's; the stage refilled below has been read by all
+      const float *tp = tile[consumed % kYZStages] + wbase;
+      f32x2 win[2 + 2 * R];
+#pragma unroll
+      for (int t = 0; t < 2 + 2 * R; ++t) win[t] = *reinterpret_cast<const f32x2 *>(tp + t * PITCH);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        f32x2 a = pack2(0.0f, 0.0f);
+#pragma unroll
+        for (int k = 0; k < NT; ++k) a = fma2(w2[k], win[c + k], a);
+        v[c] = a;
+      }
+      stage_plane();
+      ++consumed;
+    }
+    const bool emit = zin - R >= zlo;             // the output completed by this step (always < zhi inside the loop)
+    blur_z_dispatch<R>(s, acc, v, w2, emit, o0, o0 + nx2, ok0, ok1);
+    if (emit) o0 += nxy2;
+    s = s + 1 == NT ? 0 : s + 1;
+  }
+}
+
+// x pass into tmp (float4 windows), then the fused y+z pass into dst
+template <int R>
+static int blur_x_then_yz(const float *src, float *dst, float *tmp, int nx, int ny, int nz) {
+  Ctx &c = ctx();
+  if ((nx & 3) != 0 || nx < 4 || (long)nx * ny > 0x7fffffffL) return 1;
+  const long rows = (long)ny * nz;
+  blur_x_direct_kernel<R><<<c.sm_count * 8, 256, 0, c.stream>>>(src, tmp, nx, rows);
+  VT_LAUNCHED();
+  const int xt = (nx / 2 + kYZx - 1) / kYZx, yt = ((ny + 1) / 2 + kYZy - 1) / kYZy;
+  // z chunks: enough CTAs for two waves of 2 per SM, but chunks of at least 64 planes (each adds 2R halo planes)
+  int zchunks = (int)((4L * c.sm_count + (long)xt * yt - 1) / ((long)xt * yt));
+  if (zchunks < 1) zchunks = 1;
+  int zchunk = (nz + zchunks - 1) / zchunks;
+  if (zchunk < 64) zchunk = nz < 64 ? nz : 64;
+  zchunks = (nz + zchunk - 1) / zchunk;
+  const long work = (long)xt * yt * zchunks;
+  if (work > 0x7fffffffL) return 1;
+  blur_yz_kernel<R><<<(unsigned int)work, kYZx * kYZy, 0, c.stream>>>(tmp, dst, nx, ny, nz, xt, yt, zchunk);
+  VT_LAUNCHED();
+  return 0;
+}
+
 // x+y fused pass into tmp, then the z pass into dst
 template <int R>
 static int blur_two_pass(const float *src, float *dst, float *tmp, int nx, int ny, int nz) {
@@ -402,6 +573,21 @@ int k_blur(const float *src, float *dst, float *tmp, int nx, int ny, int nz, con
   if (grid < 1) grid = 1;
   // x: src -> dst ; y: dst -> tmp ; z: tmp -> dst
   prof_begin(PK_BLUR);
+  const char *bmode = getenv("VOLTOOL_BLUR_MODE");   // "yz": x pass + fused y/z pass; default: fused x/y pass + z pass
+  if (bmode && !strcmp(bmode, "yz")) {
+    int rc = 1;
+    switch (R) {
+      case 1: rc = blur_x_then_yz<1>(src, dst, tmp, nx, ny, nz); break;
+      case 2: rc = blur_x_then_yz<2>(src, dst, tmp, nx, ny, nz); break;
+      case 3: rc = blur_x_then_yz<3>(src, dst, tmp, nx, ny, nz); break;
+      case 4: rc = blur_x_then_yz<4>(src, dst, tmp, nx, ny, nz); break;
+      case 5: rc = blur_x_then_yz<5>(src, dst, tmp, nx, ny, nz); break;
+      case 6: rc = blur_x_then_yz<6>(src, dst, tmp, nx, ny, nz); break;
+      default: break;
+    }
+    if (rc == 0) { prof_end(PK_BLUR); return 0; }
+    if (rc > 1) return rc;
+  }
   if (!getenv("VOLTOOL_BLUR_GENERIC") && !getenv("VOLTOOL_BLUR_SEPARATE")) {
     int rc = 1;
     switch (R) {
