@@ -156,3 +156,34 @@ def test_fit_overlap_equals_serial(monkeypatch):
         ctx.close()
     assert np.array_equal(bits(out["0"]), bits(out["1"]))
     assert np.isfinite(out["1"]).all() and out["1"].max() > 0.5
+
+
+def test_fit_list_overflow_falls_back_to_cooperative_splat(monkeypatch):
+    """a tile list that does not fit its slot is never truncated: the call notices the flag and redoes the
+    poses with the block-cooperative splat kernel -- the bits of a context that was told to use that kernel
+    from the start, and the list kernel's values to rounding"""
+    pos, radii, mass = make_structure(5000, 22.0, seed=61, center=(36.0, 36.0, 36.0))
+    radscale, gsp, quality = vt.sim_policy(5.0)
+    com = vt.measure_center(pos, mass)
+    T = vt.sim(vt.pose_apply(pos, com, (48.0, 0.0, 24.0)), radii, quality, radscale, 1.0)
+    rots = (np.random.default_rng(62).integers(0, 15, size=(150, 3)) * 24).astype(np.float32)
+    poses = vt.FitContext.make_poses(rots)
+    monkeypatch.setenv("VOLTOOL_FIT_BATCH", "64")
+    ctx = vt.FitContext(pos, radii, T, 5.0)
+    want = ctx.eval_poses(com, poses).copy()
+    ctx.close()
+    monkeypatch.setenv("VOLTOOL_LIST_CAP", "32")          # far below the fullest tile
+    ctx = vt.FitContext(pos, radii, T, 5.0)
+    got = ctx.eval_poses(com, poses).copy()
+    again = ctx.eval_poses(com, poses)                       # the context stays on the fallback
+    ctx.close()
+    assert np.array_equal(bits(again), bits(got))
+    # the two splat kernels group their partial sums differently: same support, values within the float
+    # rounding of a few dozen additions (both are within 1e-5 of the oracle, test_gpu_parity)
+    assert np.max(np.abs(got - want) / np.abs(want)) < 2e-6
+    monkeypatch.delenv("VOLTOOL_LIST_CAP")
+    monkeypatch.setenv("VOLTOOL_SPLAT_COOP", "1")
+    ctx = vt.FitContext(pos, radii, T, 5.0)
+    coop = ctx.eval_poses(com, poses)
+    ctx.close()
+    assert np.array_equal(bits(coop), bits(got))             # fallback == cooperative kernel from the start

@@ -1,6 +1,7 @@
 // vt_splat2.cu -- barrier-free splat: per-tile atom lists (one warp per tile) + per-region
 // accumulation (one warp per 8x8x4 region).  Same arithmetic and the same deterministic
-// accumulation order as the cooperative kernel in vt_sim.cu (group order, then lane order), but no
+// accumulation order per voxel as the cooperative kernel in vt_sim.cu up to how partial sums are grouped
+// (group order, then lane order; the two agree to a few 1e-7 relative, tests/test_gpu_fullsize.py), but no
 // block barrier anywhere, so unevenly filled regions do not stall one another:
 //
 //   atom_box_kernel   per (pose, atom): the reference's truncated integer box, packed 3 x (lo|hi<<16)
@@ -12,6 +13,7 @@
 //
 // A tile whose list would overflow its slot sets a flag; the caller then reruns the batch with the
 // cooperative kernel (no silent truncation).
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -318,6 +320,7 @@ int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb) {
   for (int v : cnt) mx = v > mx ? v : mx;
   int cap = (int)(1.6 * mx) + 128;
   cap = (cap + 127) & ~127;
+  if (const char *force = getenv("VOLTOOL_LIST_CAP")) cap = std::max(32, atoi(force));   // tests: provoke the overflow fallback
   const size_t bytes = sizeof(unsigned int) * (size_t)pb.B * pb.tiles_cap * cap;
   if (bytes > ((size_t)12 << 30)) return 0;  // would not pay: keep the cooperative kernel
   if (dev_alloc((void **)&pb.d_tlist, bytes)) return 2;
