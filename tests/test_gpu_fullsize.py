@@ -187,3 +187,28 @@ def test_fit_list_overflow_falls_back_to_cooperative_splat(monkeypatch):
     coop = ctx.eval_poses(com, poses)
     ctx.close()
     assert np.array_equal(bits(coop), bits(got))             # fallback == cooperative kernel from the start
+
+
+def test_sim_list_estimate_and_overflow(monkeypatch):
+    """vt_sim sizes its tile lists from the mean tile fill (no counting pass); a list that does not fit makes
+    the call fall back to the cooperative kernel -- also for a structure far denser in one corner than on
+    average, which is what defeats the estimate"""
+    pos, radii, _ = make_structure(20000, 30.0, seed=71)
+    clump = (np.random.default_rng(72).random((6000, 3)) * 6.0 + 70.0).astype(np.float32)   # 6000 atoms in a 6 A cube
+    pos2 = np.concatenate([pos, clump]).astype(np.float32)
+    rad2 = np.concatenate([radii, np.full(6000, 1.5, np.float32)])
+    radscale, gsp, quality = vt.sim_policy(5.0)
+    for p_, r_ in ((pos, radii), (pos2, rad2)):
+        want = vt.sim(p_, r_, quality, radscale, gsp)
+        monkeypatch.setenv("VOLTOOL_SPLAT_COOP", "1")
+        coop = vt.sim(p_, r_, quality, radscale, gsp)
+        monkeypatch.delenv("VOLTOOL_SPLAT_COOP")
+        monkeypatch.setenv("VOLTOOL_LIST_CAP", "32")
+        forced = vt.sim(p_, r_, quality, radscale, gsp)
+        monkeypatch.delenv("VOLTOOL_LIST_CAP")
+        a, b, c = want.data, coop.data, forced.data
+        assert want.grid.astuple() == coop.grid.astuple() == forced.grid.astuple()
+        assert np.array_equal(bits(b), bits(c))                       # forced overflow == cooperative kernel
+        assert np.array_equal(a != 0, b != 0)                         # identical support
+        nz = a != 0
+        assert np.max(np.abs(a[nz] - b[nz]) / np.abs(b[nz])) < 1e-5      # each kernel is within 1e-5 of the oracle

@@ -83,18 +83,22 @@ int sim_to_map(const float *pos, const float *radii, long natoms, int quality, f
   if (!rc) rc = dev_alloc((void **)&pb.d_bitmap, sizeof(unsigned int) * (size_t)pb.tiles_cap * ((as.ngroups + 31) / 32));
   const float com0[3] = {0.f, 0.f, 0.f};
   if (!rc) rc = batch_prepare(as, pb, 1, nullptr, com0, 1, nullptr);
-  if (!rc) rc = batch_calibrate_lists(as, pb);
+  if (!rc) rc = batch_estimate_lists(as, pb, nv);
   if (!rc) rc = batch_splat(as, pb, 1);
-  if (!rc && pb.use_lists) {
-    int ovf = 0;
-    rc = batch_lists_overflowed(pb, &ovf);
-    if (!rc && ovf) { pb.use_lists = false; rc = batch_splat(as, pb, 1); }
-  }
+  // one round trip for the overflow flag and the geometry
   PoseGeom G;
-  if (!rc) {
+  int totals[4] = {0, 0, 0, 0};
+  auto readback = [&]() -> int {
     cudaError_t e = cudaMemcpyAsync(&G, pb.d_geom, sizeof(G), cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(totals, pb.d_totals, sizeof(totals), cudaMemcpyDeviceToHost, c.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
-    if (e != cudaSuccess) rc = cuda_fail(e, "sim readback", __FILE__, __LINE__);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "sim readback", __FILE__, __LINE__);
+  };
+  if (!rc) rc = readback();
+  if (!rc && pb.use_lists && totals[2]) {   // a tile list did not fit: redo with the cooperative kernel
+    pb.use_lists = false;
+    rc = batch_splat(as, pb, 1);
+    if (!rc) rc = readback();
   }
   if (!rc && (G.nv[0] != nv[0] || G.nv[1] != nv[1] || G.nv[2] != nv[2])) {
     set_error("vt_sim: host/device grid mismatch (%d %d %d vs %d %d %d)", nv[0], nv[1], nv[2], G.nv[0], G.nv[1], G.nv[2]);

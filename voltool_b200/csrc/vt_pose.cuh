@@ -100,6 +100,8 @@ int batch_splat(const AtomSet &as, PoseBatch &pb, int npose);
 // size and switch on the list-based splat from the pose(s) currently prepared in pb (needs
 // batch_prepare first); leaves the cooperative kernel in place when it does not apply
 int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb);
+// single-pose variant without the counting pass (slot sized from the mean tile fill); nv = sim grid size
+int batch_estimate_lists(const AtomSet &as, PoseBatch &pb, const int nv[3]);
 int batch_splat_lists(const AtomSet &as, PoseBatch &pb, int npose);
 // the splat in two halves, so that a caller can run the list building of the next batch on a second
 // stream while this batch accumulates: front = tile bitmaps (+ boxes and per-tile lists), back = the

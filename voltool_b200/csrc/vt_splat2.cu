@@ -329,6 +329,32 @@ int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb) {
   return 0;
 }
 
+// Single structure (vt_sim): no counting pass.  The slot is sized from the mean number of atoms whose
+// box can reach a tile (x4 for the denser interior of the structure); if a tile overflows anyway the
+// caller falls back to the cooperative kernel, as everywhere.
+int batch_estimate_lists(const AtomSet &as, PoseBatch &pb, const int nv[3]) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  pb.use_lists = false;
+  if (pb.B != 1 || getenv("VOLTOOL_SPLAT_COOP") || as.n >= (1 << 24) || pb.cap_n > 65535) return 0;
+  const double h = std::ceil((double)as.prm.gausslim * as.maxrad * as.prm.radscale * as.prm.invgs) + 1.0;
+  const double reach = (kTX + 2 * h) * (kTY + 2 * h) * (kTZ + 2 * h);
+  const double mean = (double)as.n * reach / ((double)nv[0] * nv[1] * nv[2]);
+  long cap = (long)(4.0 * mean) + 256;
+  cap = std::min<long>(cap, ((long)as.n + 127) & ~127L);
+  cap = (cap + 127) & ~127L;
+  if (const char *force = getenv("VOLTOOL_LIST_CAP")) cap = std::max(32, atoi(force));
+  const size_t bytes = sizeof(unsigned int) * (size_t)pb.tiles_cap * (size_t)cap;
+  if (bytes > ((size_t)4 << 30)) return 0;
+  if (dev_alloc((void **)&pb.d_boxes, sizeof(uint3) * (size_t)as.n)) return 2;
+  if (dev_alloc((void **)&pb.d_tcount, sizeof(int) * (size_t)pb.tiles_cap)) return 2;
+  if (dev_alloc((void **)&pb.d_tlist, bytes)) return 2;
+  VT_CUDA(cudaMemsetAsync(pb.d_totals + 2, 0, sizeof(int), c.stream));
+  pb.cap_t = (int)cap;
+  pb.use_lists = true;
+  return 0;
+}
+
 // returns 0 on launch; the overflow flag (d_totals[2]) must be checked by the caller after a sync
 int batch_lists_front(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
