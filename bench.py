@@ -446,7 +446,31 @@ def extra_ops(vt, peaks, args):
     vt.sync()
     dt = (time.perf_counter() - t0) / reps
     res["sim_cc_cfg1"] = {"voxels": S.gridsize(), "s_per_call": dt, "voxels_per_s": S.gridsize() / dt, "cc": cc,
-                          "note": "host call incl. atom sort/upload"}
+                          "note": "vt_sim_cc through the C ABI with host coordinates (atom sort + upload + splat + cc + readback)"}
+    # the same call with the library's own events around its kernels: what the device spends
+    vt.profile_reset(); vt.profile_enable(True)
+    for _ in range(reps):
+        vt.sim_cc(pos, radii, 5.0, S, gspacing=1.0)
+    vt.sync()
+    kms = sum(vt.profile_get(k)[0] for k in ("transform", "setup", "splat", "cc")) / reps
+    vt.profile_enable(False)
+    res["sim_cc_cfg1"]["kernel_ms_per_call"] = kms
+    res["sim_cc_cfg1"]["kernel_voxels_per_s"] = S.gridsize() / (kms * 1e-3) if kms > 0 else None
+    if not args.no_cpu:
+        # the reference's CPU path on the same input: restated splat (OpenMP) + the reference's cc_threaded
+        try:
+            from oracle.pyoracle import Grid as OGrid
+            lib, kind = load_reference()
+            threads = cpu_threads()
+            if kind == "reference":
+                lib.set_numprocs(threads)
+            t0 = time.perf_counter()
+            og, od = lib.sim(pos, radii, quality, radscale, 1.0, nthreads=threads)
+            ccr = lib.ref_cc(og, od, og, od, -3.4028234663852886e38) if kind == "reference" else lib.cc(og, od, og, od, nthreads=threads)
+            dtc = time.perf_counter() - t0
+            res["sim_cc_cfg1"]["cpu"] = {"s_per_call": dtc, "voxels_per_s": og.n / dtc, "cores": threads, "kind": kind, "cc": ccr}
+        except Exception as e:  # the checker is optional for this leg
+            res["sim_cc_cfg1"]["cpu"] = {"unavailable": str(e)[:200]}
     return res
 
 
