@@ -212,3 +212,11 @@ def test_sim_list_estimate_and_overflow(monkeypatch):
         assert np.array_equal(a != 0, b != 0)                         # identical support
         nz = a != 0
         assert np.max(np.abs(a[nz] - b[nz]) / np.abs(b[nz])) < 1e-5      # each kernel is within 1e-5 of the oracle
+
+
+def test_fit_rejects_skewed_target():
+    pos, radii, mass = make_structure(300, 8.0, seed=81)
+    g = vt.Grid.make((0.0, 0.0, 0.0), (24, 24, 24), axes=((23.0, 1.0, 0.0), (0.0, 23.0, 0.5), (0.0, 0.0, 23.0)))
+    T = vt.VolMap(g, np.random.default_rng(82).random(g.n, dtype=np.float32))
+    with pytest.raises(vt.VoltoolGpuError):
+        vt.FitContext(pos, radii, T, 5.0)

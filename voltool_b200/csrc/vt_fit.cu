@@ -309,6 +309,19 @@ int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_ma
                   vt_fit_ctx **out) {
   VT_REQUIRE_CTX();
   if (!pos || !radii || !target || natoms <= 0) { set_error("vt_fit_create: bad arguments"); return 1; }
+  {
+    // the batched cc kernel is the separable one: a skewed target cell would make every pose's CC undefined,
+    // so say so here (the reference's own two-map code assumes orthogonal axis-aligned cells, Voltool.C:55-56)
+    float tinv[16];
+    geom::grid_inverse(target->grid, false, tinv);
+    const vt_grid &tg = target->grid;
+    const bool aligned = tg.xaxis[1] == 0 && tg.xaxis[2] == 0 && tg.yaxis[0] == 0 && tg.yaxis[2] == 0 && tg.zaxis[0] == 0 &&
+                         tg.zaxis[1] == 0;
+    if (!aligned || !geom::diagonal_inverse(tinv)) {
+      set_error("vt_fit_create: the target map must have an orthogonal, axis-aligned cell");
+      return 1;
+    }
+  }
   if ((long)target->grid.xsize * target->grid.ysize >= (1L << 30)) {
     set_error("vt_fit_create: target planes of 2^30 voxels or more are not supported");
     return 1;
