@@ -380,7 +380,7 @@ def test_supersample_known_answers():
     assert np.all(const == 2.5)
 
 
-@pytest.mark.parametrize("mode", ["", "yz"])
+@pytest.mark.parametrize("mode", ["", "yz", "xyz"])
 @pytest.mark.parametrize("sigma", [0.6, 1.5, 2.0])
 def test_blur_bit_exact(oracle, sigma, mode, monkeypatch):
     """default path and the x | y+z form (z pass as a register scatter), incl. maps thinner than the radius"""
