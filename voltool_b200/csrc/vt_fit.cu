@@ -77,7 +77,7 @@ int sim_to_map(const float *pos, const float *radii, long natoms, int quality, f
   if (!rc) rc = dev_alloc((void **)&pb.d_tgroup, sizeof(float4) * (size_t)as.ngroups);
   if (!rc) rc = dev_alloc((void **)&pb.d_bbox, sizeof(unsigned int) * 6);
   if (!rc) rc = dev_alloc((void **)&pb.d_geom, sizeof(PoseGeom));
-  if (!rc) rc = dev_alloc((void **)&pb.d_totals, sizeof(int) * 4);
+  if (!rc) rc = dev_alloc((void **)&pb.d_totals, sizeof(int) * 8);
   if (!rc) rc = dev_alloc((void **)&pb.d_grid, sizeof(float) * (size_t)cells);
   pb.tiles_cap = ((nv[0] + kTX - 1) / kTX) * ((nv[1] + kTY - 1) / kTY) * ((nv[2] + kTZ - 1) / kTZ);
   if (!rc) rc = dev_alloc((void **)&pb.d_bitmap, sizeof(unsigned int) * (size_t)pb.tiles_cap * ((as.ngroups + 31) / 32));
@@ -346,6 +346,7 @@ int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_ma
       const float com0[3] = {0.f, 0.f, 0.f};
       rc = batch_prepare(f->as, f->pb[k], 1, nullptr, com0, 1, &target->grid);
       if (!rc) rc = batch_calibrate_lists(f->as, f->pb[k]);
+      if (f->nslots > 1) f->pb[k].splat_ctas = 4;   // leave room for the second stream (vt_splat2.cu)
     }
   }
   if (!rc && f->nslots > 1) {

@@ -79,6 +79,7 @@ struct PoseBatch {
   int *d_tcount = nullptr;           // [B][tiles_cap]
   int cap_t = 0;
   bool use_lists = false;
+  int splat_ctas = 0;                // resident splat CTAs per SM (0: default)
   float *d_grid = nullptr;
   geom::AxisEntry *d_tab = nullptr;  // [B][6][cap_o]
   double *d_part = nullptr;          // [B][cap_items][6]

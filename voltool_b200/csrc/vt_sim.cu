@@ -221,7 +221,7 @@ int batch_create(const AtomSet &as, const vt_grid *target, int B, PoseBatch &pb)
   if (dev_alloc((void **)&pb.d_tgroup, sizeof(float4) * (size_t)B * as.ngroups)) return 2;
   if (dev_alloc((void **)&pb.d_bbox, sizeof(unsigned int) * 6 * B)) return 2;
   if (dev_alloc((void **)&pb.d_geom, sizeof(PoseGeom) * B)) return 2;
-  if (dev_alloc((void **)&pb.d_totals, sizeof(int) * 4)) return 2;
+  if (dev_alloc((void **)&pb.d_totals, sizeof(int) * 8)) return 2;
   {
     const int tn = (pb.cap_n + kTX - 1) / kTX, tm = (pb.cap_n + kTY - 1) / kTY, tk = (pb.cap_n + kTZ - 1) / kTZ;
     pb.tiles_cap = tn * tm * tk;
@@ -380,6 +380,8 @@ __global__ void __launch_bounds__(256) pose_setup_kernel(const unsigned int *__r
     totals[0] = t;
     totals[1] = c;
     totals[3] = 0;
+    totals[4] = 0;   // work queues of the splat and cc kernels of this batch (warps draw tasks with atomicAdd)
+    totals[5] = 0;
   }
 }
 
@@ -765,8 +767,13 @@ __global__ void __launch_bounds__(256, 2) pose_cc_kernel(const PoseGeom *__restr
                                                       long cap_items, float thr_f, double *__restrict__ part) {
   const int lane = threadIdx.x & 31;
   const int total = totals[1];
-  const int wstride = gridDim.x * 8;
-  for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < total; item += wstride) {
+  int *queue = const_cast<int *>(totals) + 5;
+  while (true) {
+    // items cost very different amounts (empty corners vs the dense interior): warps draw them from a queue
+    int item = 0;
+    if (lane == 0) item = atomicAdd(queue, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
     const int p = find_pose(geo, npose, item, true);
     const PoseGeom &G = geo[p];
     const int local = item - G.cc_base;
@@ -827,7 +834,8 @@ int batch_cc(PoseBatch &pb, int npose, const vt_map *target, double threshold, f
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
   prof_begin(PK_POSE_CC);
-  pose_cc_kernel<<<c.sm_count * 8, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, pb.d_grid, pb.cap_grid, target->d,
+  static int cc_per_sm = getenv("VOLTOOL_CC_CTAS") ? atoi(getenv("VOLTOOL_CC_CTAS")) : 2;
+  pose_cc_kernel<<<c.sm_count * cc_per_sm, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, pb.d_grid, pb.cap_grid, target->d,
                                                        target->grid.xsize, target->grid.ysize, pb.d_tab, pb.cap_o,
                                                        pb.cap_items, threshold_as_float(threshold), pb.d_part);
   prof_end(PK_POSE_CC);

@@ -165,10 +165,15 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int lt = (1u << lane) - 1u;
   const long ntask = (long)totals[0] * kSplatWarps;
-  const long stride = (long)gridDim.x * 4;
+  int *queue = const_cast<int *>(totals) + 4;
   const int ly = lane & 7, lz = lane >> 3;
   float *rec = s_rec[warp];
-  for (long task = (long)blockIdx.x * 4 + warp; task < ntask; task += stride) {
+  while (true) {
+    // regions cost very different amounts (empty corners vs the dense interior): warps draw them from a queue
+    int task = 0;
+    if (lane == 0) task = atomicAdd(queue, 1);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= ntask) break;
     const int item = (int)(task / kSplatWarps), region = (int)(task - (long)item * kSplatWarps);
     const int p = find_pose_tile(geo, npose, item);
     const PoseGeom &G = geo[p];
@@ -376,7 +381,13 @@ int batch_lists_back(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
   prof_begin(PK_SPLAT);
-  splat_list_kernel<<<c.sm_count * 6 * 4, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, pb.d_tpos, as.d_const,
+  // persistent: the warps draw their tasks from a queue, so one resident set of CTAs is enough (6 fit an SM).
+  // The fit pipeline asks for 4 per SM: the kernel saturates the shared-memory pipe long before it runs out
+  // of warps, and the free third of each SM is where the list building of the next batch runs beside it
+  // (measured 6 / 5 / 4 / 3 per SM: 35.0 / 35.5 / 36.9 / 33.2 k poses/s)
+  static const int forced = getenv("VOLTOOL_SPLAT_CTAS") ? atoi(getenv("VOLTOOL_SPLAT_CTAS")) : 0;
+  const int per_sm = forced > 0 ? forced : (pb.splat_ctas > 0 ? pb.splat_ctas : 6);
+  splat_list_kernel<<<c.sm_count * per_sm, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, pb.d_tpos, as.d_const,
                                                               pb.d_boxes, pb.d_tlist, pb.d_tcount, pb.cap_t, pb.tiles_cap,
                                                               as.prm.gs, pb.d_grid, pb.cap_grid);
   prof_end(PK_SPLAT);
