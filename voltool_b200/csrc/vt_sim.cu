@@ -380,8 +380,9 @@ __global__ void __launch_bounds__(256) pose_setup_kernel(const unsigned int *__r
     totals[0] = t;
     totals[1] = c;
     totals[3] = 0;
-    totals[4] = 0;   // work queues of the splat and cc kernels of this batch (warps draw tasks with atomicAdd)
+    totals[4] = 0;   // work queues of the splat, cc and gather kernels of this batch (warps draw tasks with atomicAdd)
     totals[5] = 0;
+    totals[6] = 0;
   }
 }
 

@@ -75,8 +75,12 @@ __global__ void __launch_bounds__(128) gather_kernel(const PoseGeom *__restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int lt = (1u << lane) - 1u;
   const int total = totals[0];
-  const int nwarps = gridDim.x * 4;
-  for (int item = blockIdx.x * 4 + warp; item < total; item += nwarps) {
+  int *queue = const_cast<int *>(totals) + 6;
+  while (true) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(queue, 1);   // tiles differ a lot in how many groups reach them
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
     const int p = find_pose_tile(geo, npose, item);
     const PoseGeom &G = geo[p];
     const int local = item - G.tile_base;
@@ -315,6 +319,7 @@ int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb) {
   atom_box_kernel<<<dim3(gx, 1), 256, 0, c.stream>>>(pb.d_geom, as.n, pb.d_tpos, as.d_const, as.prm.invgs, pb.d_boxes);
   VT_LAUNCHED();
   VT_CUDA(cudaMemsetAsync(pb.d_tcount, 0, sizeof(int) * (size_t)pb.tiles_cap, c.stream));
+  VT_CUDA(cudaMemsetAsync(pb.d_totals + 6, 0, sizeof(int), c.stream));   // the gather work queue (else reset by pose_setup)
   gather_kernel<<<c.sm_count * 8, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, 1, as.n, pb.d_bitmap, pb.tiles_cap, nwords,
                                                       pb.d_boxes, nullptr, pb.d_tcount, 0, pb.d_totals + 3);
   VT_LAUNCHED();
