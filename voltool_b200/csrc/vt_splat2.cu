@@ -128,14 +128,13 @@ __global__ void __launch_bounds__(128) gather_kernel(const PoseGeom *__restrict_
                           ymax >= y0 && zmin <= z0 + kTZ - 1 && zmax >= z0;
         int mask = 0;
         if (take) {
-          // bit w: box meets region w (x half w&1, z half (w>>1)&1, y block w>>2)
-          const int mx = (xmin <= x0 + 7 ? 1 : 0) | (xmax >= x0 + 8 ? 2 : 0);
-          const int mz = (zmin <= z0 + 3 ? 1 : 0) | (zmax >= z0 + 4 ? 2 : 0);
-#pragma unroll
-          for (int w = 0; w < kSplatWarps; ++w) {
-            const int yb = y0 + 8 * (w >> 2);
-            if (((mx >> (w & 1)) & 1) && ((mz >> ((w >> 1) & 1)) & 1) && ymin <= yb + 7 && ymax >= yb) mask |= 1 << w;
-          }
+          // bit w: box meets region w (x half w&1, z half (w>>1)&1, y block w>>2): the AND of three
+          // byte patterns, one per axis, each the OR of the halves the box reaches
+          static_assert(kSplatWarps == 8, "region masks are written for 2 x 2 x 2 regions per tile");
+          const int bx_ = (xmin <= x0 + 7 ? 0x55 : 0) | (xmax >= x0 + 8 ? 0xaa : 0);
+          const int bz_ = (zmin <= z0 + 3 ? 0x33 : 0) | (zmax >= z0 + 4 ? 0xcc : 0);
+          const int by_ = (ymin <= y0 + 7 ? 0x0f : 0) | (ymax >= y0 + 8 ? 0xf0 : 0);
+          mask = bx_ & bz_ & by_;
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, take);
         if (take) {
