@@ -70,7 +70,7 @@ struct PoseBatch {
   float4 *d_tgroup = nullptr;
   unsigned int *d_bbox = nullptr;
   PoseGeom *d_geom = nullptr;
-  int *d_totals = nullptr;  // [0] tiles, [1] cc items
+  int *d_totals = nullptr;  // [0] tiles, [1] cc items, [2] list overflow flag, [3] calibration scratch, [4..6] task queues (splat, cc, gather)
   unsigned int *d_bitmap = nullptr;  // [B][tiles_cap][ceil(ngroups/32)]: groups that can reach a tile
   int tiles_cap = 0;
   // barrier-free splat (vt_splat2.cu): packed integer boxes, per-tile atom lists

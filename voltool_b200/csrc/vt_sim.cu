@@ -765,10 +765,10 @@ __global__ void __launch_bounds__(256, 2) pose_cc_kernel(const PoseGeom *__restr
                                                       int npose, const float *__restrict__ grid_all, long cap_grid,
                                                       const float *__restrict__ tdata, int tnx, int tny,
                                                       const geom::AxisEntry *__restrict__ tab_all, int cap_o,
-                                                      long cap_items, float thr_f, double *__restrict__ part) {
+                                                      long cap_items, float thr_f, double *__restrict__ part, int *queues) {
   const int lane = threadIdx.x & 31;
   const int total = totals[1];
-  int *queue = const_cast<int *>(totals) + 5;
+  int *queue = queues + 1;
   while (true) {
     // items cost very different amounts (empty corners vs the dense interior): warps draw them from a queue
     int item = 0;
@@ -838,7 +838,7 @@ int batch_cc(PoseBatch &pb, int npose, const vt_map *target, double threshold, f
   static int cc_per_sm = getenv("VOLTOOL_CC_CTAS") ? atoi(getenv("VOLTOOL_CC_CTAS")) : 2;
   pose_cc_kernel<<<c.sm_count * cc_per_sm, 256, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, pb.d_grid, pb.cap_grid, target->d,
                                                        target->grid.xsize, target->grid.ysize, pb.d_tab, pb.cap_o,
-                                                       pb.cap_items, threshold_as_float(threshold), pb.d_part);
+                                                       pb.cap_items, threshold_as_float(threshold), pb.d_part, pb.d_totals + 4);
   prof_end(PK_POSE_CC);
   VT_LAUNCHED();
   pose_cc_finish_kernel<<<npose, 256, 0, c.stream>>>(pb.d_geom, pb.d_part, pb.cap_items, d_cc, d_sums);

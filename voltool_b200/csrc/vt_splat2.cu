@@ -70,12 +70,12 @@ __global__ void __launch_bounds__(128) gather_kernel(const PoseGeom *__restrict_
                                                      int npose, int natoms, const unsigned int *__restrict__ bitmap,
                                                      int tiles_cap, int nwords, const uint3 *__restrict__ boxes,
                                                      unsigned int *__restrict__ tlist, int *__restrict__ tcount,
-                                                     int cap_t, int *__restrict__ overflow) {
+                                                     int cap_t, int *__restrict__ overflow, int *queues) {
   __shared__ unsigned short s_gl[4][kGlist];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int lt = (1u << lane) - 1u;
   const int total = totals[0];
-  int *queue = const_cast<int *>(totals) + 6;
+  int *queue = queues + 2;
   while (true) {
     int item = 0;
     if (lane == 0) item = atomicAdd(queue, 1);   // tiles differ a lot in how many groups reach them
@@ -162,13 +162,14 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
                                                             const uint3 *__restrict__ boxes,
                                                             const unsigned int *__restrict__ tlist,
                                                             const int *__restrict__ tcount, int cap_t, int tiles_cap,
-                                                            float gs, float *__restrict__ grid_all, long cap_grid) {
+                                                            float gs, float *__restrict__ grid_all, long cap_grid,
+                                                            int *queues) {
   __shared__ __align__(16) float s_rec[4][32 * kRec2];
   __shared__ int s_pend[4][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int lt = (1u << lane) - 1u;
   const long ntask = (long)totals[0] * kSplatWarps;
-  int *queue = const_cast<int *>(totals) + 4;
+  int *queue = queues;
   const int ly = lane & 7, lz = lane >> 3;
   float *rec = s_rec[warp];
   while (true) {
@@ -320,7 +321,7 @@ int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb) {
   VT_CUDA(cudaMemsetAsync(pb.d_tcount, 0, sizeof(int) * (size_t)pb.tiles_cap, c.stream));
   VT_CUDA(cudaMemsetAsync(pb.d_totals + 6, 0, sizeof(int), c.stream));   // the gather work queue (else reset by pose_setup)
   gather_kernel<<<c.sm_count * 8, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, 1, as.n, pb.d_bitmap, pb.tiles_cap, nwords,
-                                                      pb.d_boxes, nullptr, pb.d_tcount, 0, pb.d_totals + 3);
+                                                      pb.d_boxes, nullptr, pb.d_tcount, 0, pb.d_totals + 3, pb.d_totals + 4);
   VT_LAUNCHED();
   std::vector<int> cnt(pb.tiles_cap);
   VT_CUDA(cudaMemcpyAsync(cnt.data(), pb.d_tcount, sizeof(int) * pb.tiles_cap, cudaMemcpyDeviceToHost, c.stream));
@@ -375,7 +376,7 @@ int batch_lists_front(const AtomSet &as, PoseBatch &pb, int npose) {
   atom_box_kernel<<<dim3(gx, npose), 256, 0, c.stream>>>(pb.d_geom, as.n, pb.d_tpos, as.d_const, as.prm.invgs, pb.d_boxes);
   VT_LAUNCHED();
   gather_kernel<<<c.sm_count * 8, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, pb.d_bitmap, pb.tiles_cap, nwords,
-                                                      pb.d_boxes, pb.d_tlist, pb.d_tcount, pb.cap_t, pb.d_totals + 2);
+                                                      pb.d_boxes, pb.d_tlist, pb.d_tcount, pb.cap_t, pb.d_totals + 2, pb.d_totals + 4);
   prof_end(PK_SETUP);
   VT_LAUNCHED();
   return 0;
@@ -393,7 +394,7 @@ int batch_lists_back(const AtomSet &as, PoseBatch &pb, int npose) {
   const int per_sm = forced > 0 ? forced : (pb.splat_ctas > 0 ? pb.splat_ctas : 6);
   splat_list_kernel<<<c.sm_count * per_sm, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, pb.d_tpos, as.d_const,
                                                               pb.d_boxes, pb.d_tlist, pb.d_tcount, pb.cap_t, pb.tiles_cap,
-                                                              as.prm.gs, pb.d_grid, pb.cap_grid);
+                                                              as.prm.gs, pb.d_grid, pb.cap_grid, pb.d_totals + 4);
   prof_end(PK_SPLAT);
   VT_LAUNCHED();
   return 0;
