@@ -346,7 +346,7 @@ int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_ma
       const float com0[3] = {0.f, 0.f, 0.f};
       rc = batch_prepare(f->as, f->pb[k], 1, nullptr, com0, 1, &target->grid);
       if (!rc) rc = batch_calibrate_lists(f->as, f->pb[k]);
-      if (f->nslots > 1) f->pb[k].splat_ctas = 4;   // leave room for the second stream (vt_splat2.cu)
+      if (f->nslots > 1) f->pb[k].splat_ctas = 5;   // leave room for the second stream (vt_splat2.cu)
     }
   }
   if (!rc && f->nslots > 1) {

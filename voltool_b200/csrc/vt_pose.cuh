@@ -75,6 +75,7 @@ struct PoseBatch {
   int tiles_cap = 0;
   // barrier-free splat (vt_splat2.cu): packed integer boxes, per-tile atom lists
   uint3 *d_boxes = nullptr;          // [B][natoms]
+  uint3 *d_gbox = nullptr;           // [B][ngroups]: union of the boxes of a group's atoms (same packing; lo > hi: empty)
   unsigned int *d_tlist = nullptr;   // [B][tiles_cap][cap_t]: id | region mask << 24
   int *d_tcount = nullptr;           // [B][tiles_cap]
   int cap_t = 0;

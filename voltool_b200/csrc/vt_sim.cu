@@ -238,7 +238,7 @@ int batch_create(const AtomSet &as, const vt_grid *target, int B, PoseBatch &pb)
 
 void batch_destroy(PoseBatch &pb) {
   dev_free(pb.d_tpos); dev_free(pb.d_tgroup); dev_free(pb.d_bbox); dev_free(pb.d_geom); dev_free(pb.d_totals); dev_free(pb.d_bitmap);
-  dev_free(pb.d_boxes); dev_free(pb.d_tlist); dev_free(pb.d_tcount);
+  dev_free(pb.d_boxes); dev_free(pb.d_gbox); dev_free(pb.d_tlist); dev_free(pb.d_tcount);
   dev_free(pb.d_grid); dev_free(pb.d_prep); dev_free(pb.d_tab); dev_free(pb.d_part);
   pb = PoseBatch();
 }
@@ -728,10 +728,8 @@ static bool lists_on(const PoseBatch &pb) { return pb.use_lists && !getenv("VOLT
 
 int batch_splat_front(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
-  int rc = batch_bin(as, pb, npose);
-  if (rc) return rc;
-  if (lists_on(pb)) return batch_lists_front(as, pb, npose);
-  return 0;
+  if (lists_on(pb)) return batch_lists_front(as, pb, npose);   // boxes -> tile bitmaps from the group boxes -> lists
+  return batch_bin(as, pb, npose);                              // tile bitmaps from the group spheres
 }
 
 int batch_splat_back(const AtomSet &as, PoseBatch &pb, int npose) {

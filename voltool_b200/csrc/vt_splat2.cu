@@ -40,27 +40,92 @@ __device__ __forceinline__ int find_pose_tile(const PoseGeom *__restrict__ geo, 
 __global__ void __launch_bounds__(256) atom_box_kernel(const PoseGeom *__restrict__ geo, int natoms,
                                                        const float4 *__restrict__ tpos_all,
                                                        const float4 *__restrict__ cst, float invgs,
-                                                       uint3 *__restrict__ boxes) {
+                                                       uint3 *__restrict__ boxes, uint3 *__restrict__ gboxes, int ngroups) {
   const int p = blockIdx.y;
   const PoseGeom &G = geo[p];
   const float ox = G.org[0], oy = G.org[1], oz = G.org[2];
   const int nv0 = G.nv[0], nv1 = G.nv[1], nv2 = G.nv[2];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < natoms; i += gridDim.x * blockDim.x) {
-    const float4 a4 = tpos_all[(size_t)p * natoms + i];
-    const float rl = cst[i].z;
-    const float ax = a4.x - ox, ay = a4.y - oy, az = a4.z - oz;  // xyzr = pos - origin
-    float t = ax * invgs;
-    const int xmin = max(__float2int_rz(t - rl), 0), xmax = min(__float2int_rz(t + rl), nv0 - 1);
-    t = ay * invgs;
-    const int ymin = max(__float2int_rz(t - rl), 0), ymax = min(__float2int_rz(t + rl), nv1 - 1);
-    t = az * invgs;
-    const int zmin = max(__float2int_rz(t - rl), 0), zmax = min(__float2int_rz(t + rl), nv2 - 1);
-    uint3 b;
-    if (xmin > xmax || ymin > ymax || zmin > zmax) b = make_uint3(1u, 1u, 1u);  // lo 1 > hi 0: empty
-    else b = make_uint3((unsigned)xmin | ((unsigned)xmax << 16), (unsigned)ymin | ((unsigned)ymax << 16),
-                        (unsigned)zmin | ((unsigned)zmax << 16));
-    boxes[(size_t)p * natoms + i] = b;
+  const int nround = (natoms + 31) & ~31;   // whole warps: a warp trip covers exactly one group of 32 atoms
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+    int xmin = 1, xmax = 0, ymin = 1, ymax = 0, zmin = 1, zmax = 0;
+    if (i < natoms) {
+      const float4 a4 = tpos_all[(size_t)p * natoms + i];
+      const float rl = cst[i].z;
+      const float ax = a4.x - ox, ay = a4.y - oy, az = a4.z - oz;  // xyzr = pos - origin
+      float t = ax * invgs;
+      xmin = max(__float2int_rz(t - rl), 0); xmax = min(__float2int_rz(t + rl), nv0 - 1);
+      t = ay * invgs;
+      ymin = max(__float2int_rz(t - rl), 0); ymax = min(__float2int_rz(t + rl), nv1 - 1);
+      t = az * invgs;
+      zmin = max(__float2int_rz(t - rl), 0); zmax = min(__float2int_rz(t + rl), nv2 - 1);
+      const bool empty = xmin > xmax || ymin > ymax || zmin > zmax;
+      boxes[(size_t)p * natoms + i] = empty ? make_uint3(1u, 1u, 1u)   // lo 1 > hi 0: empty
+                                            : make_uint3((unsigned)xmin | ((unsigned)xmax << 16), (unsigned)ymin | ((unsigned)ymax << 16),
+                                                         (unsigned)zmin | ((unsigned)zmax << 16));
+      if (empty) { xmin = ymin = zmin = 1; xmax = ymax = zmax = 0; }
+    }
+    // the group's box: union of its atoms' boxes (what pose_bin_box_kernel marks tiles with)
+    const bool has = xmin <= xmax;
+    int lo[3] = {has ? xmin : 0x7fffffff, has ? ymin : 0x7fffffff, has ? zmin : 0x7fffffff};
+    int hi[3] = {has ? xmax : -1, has ? ymax : -1, has ? zmax : -1};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = min(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+        hi[k] = max(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+      }
+    if ((threadIdx.x & 31) == 0 && gboxes) {
+      const int g = i >> 5;
+      if (g < ngroups)
+        gboxes[(size_t)p * ngroups + g] = hi[0] < 0 ? make_uint3(1u, 1u, 1u)
+                                                     : make_uint3((unsigned)lo[0] | ((unsigned)hi[0] << 16), (unsigned)lo[1] | ((unsigned)hi[1] << 16),
+                                                                  (unsigned)lo[2] | ((unsigned)hi[2] << 16));
+    }
   }
+}
+
+// Which groups can touch which tile, from the group boxes: thread per (pose, group) marks every tile its box
+// meets (atomicOr: order independent).  Integer arithmetic only, and tighter than the bounding-sphere test of
+// pose_bin_kernel (vt_sim.cu), which stays for the cooperative splat path that has no boxes.
+__global__ void __launch_bounds__(256) pose_bin_box_kernel(const PoseGeom *__restrict__ geo, int ngroups,
+                                                           const uint3 *__restrict__ gboxes,
+                                                           unsigned int *__restrict__ bitmap, int tiles_cap, int nwords) {
+  const int p = blockIdx.y;
+  const PoseGeom &G = geo[p];
+  const int ntx = G.tiles[0], nty = G.tiles[1], ntz = G.tiles[2];
+  if (ntx == 0) return;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+    const uint3 b = gboxes[(size_t)p * ngroups + g];
+    const int xmin = b.x & 0xffff, xmax = b.x >> 16, ymin = b.y & 0xffff, ymax = b.y >> 16;
+    const int zmin = b.z & 0xffff, zmax = b.z >> 16;
+    if (xmin > xmax) continue;
+    const int tx0 = xmin / kTX, tx1 = min(ntx - 1, xmax / kTX);
+    const int ty0 = ymin / kTY, ty1 = min(nty - 1, ymax / kTY);
+    const int tz0 = zmin / kTZ, tz1 = min(ntz - 1, zmax / kTZ);
+    const unsigned int bit = 1u << (g & 31);
+    for (int tz = tz0; tz <= tz1; ++tz)
+      for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx)
+          atomicOr(&bitmap[((size_t)p * tiles_cap + (tz * nty + ty) * ntx + tx) * nwords + (g >> 5)], bit);
+  }
+}
+
+// boxes, group boxes and the tile bitmaps made from them
+static int lists_boxes_and_bins(const AtomSet &as, PoseBatch &pb, int npose) {
+  Ctx &c = ctx();
+  const int nwords = (as.ngroups + 31) / 32;
+  int gx = (as.n + 255) / 256;
+  if (gx > 64) gx = 64;
+  VT_CUDA(cudaMemsetAsync(pb.d_bitmap, 0, sizeof(unsigned int) * (size_t)npose * pb.tiles_cap * nwords, c.stream));
+  atom_box_kernel<<<dim3(gx, npose), 256, 0, c.stream>>>(pb.d_geom, as.n, pb.d_tpos, as.d_const, as.prm.invgs, pb.d_boxes,
+                                                          pb.d_gbox, as.ngroups);
+  VT_LAUNCHED();
+  int gg = (as.ngroups + 255) / 256;
+  if (gg > 32) gg = 32;
+  pose_bin_box_kernel<<<dim3(gg, npose), 256, 0, c.stream>>>(pb.d_geom, as.ngroups, pb.d_gbox, pb.d_bitmap, pb.tiles_cap, nwords);
+  VT_LAUNCHED();
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------ gather
@@ -311,13 +376,10 @@ int batch_calibrate_lists(const AtomSet &as, PoseBatch &pb) {
   const int nwords = (as.ngroups + 31) / 32;
   if (dev_alloc((void **)&pb.d_boxes, sizeof(uint3) * (size_t)pb.B * as.n)) return 2;
   if (dev_alloc((void **)&pb.d_tcount, sizeof(int) * (size_t)pb.B * pb.tiles_cap)) return 2;
+  if (dev_alloc((void **)&pb.d_gbox, sizeof(uint3) * (size_t)pb.B * as.ngroups)) return 2;
   VT_CUDA(cudaMemsetAsync(pb.d_totals + 2, 0, sizeof(int), c.stream));
-  int rc = batch_bin(as, pb, 1);
+  int rc = lists_boxes_and_bins(as, pb, 1);
   if (rc) return rc;
-  int gx = (as.n + 255) / 256;
-  if (gx > 64) gx = 64;
-  atom_box_kernel<<<dim3(gx, 1), 256, 0, c.stream>>>(pb.d_geom, as.n, pb.d_tpos, as.d_const, as.prm.invgs, pb.d_boxes);
-  VT_LAUNCHED();
   VT_CUDA(cudaMemsetAsync(pb.d_tcount, 0, sizeof(int) * (size_t)pb.tiles_cap, c.stream));
   VT_CUDA(cudaMemsetAsync(pb.d_totals + 6, 0, sizeof(int), c.stream));   // the gather work queue (else reset by pose_setup)
   gather_kernel<<<c.sm_count * 8, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, 1, as.n, pb.d_bitmap, pb.tiles_cap, nwords,
@@ -357,6 +419,7 @@ int batch_estimate_lists(const AtomSet &as, PoseBatch &pb, const int nv[3]) {
   const size_t bytes = sizeof(unsigned int) * (size_t)pb.tiles_cap * (size_t)cap;
   if (bytes > ((size_t)4 << 30)) return 0;
   if (dev_alloc((void **)&pb.d_boxes, sizeof(uint3) * (size_t)as.n)) return 2;
+  if (dev_alloc((void **)&pb.d_gbox, sizeof(uint3) * (size_t)as.ngroups)) return 2;
   if (dev_alloc((void **)&pb.d_tcount, sizeof(int) * (size_t)pb.tiles_cap)) return 2;
   if (dev_alloc((void **)&pb.d_tlist, bytes)) return 2;
   VT_CUDA(cudaMemsetAsync(pb.d_totals + 2, 0, sizeof(int), c.stream));
@@ -370,11 +433,9 @@ int batch_lists_front(const AtomSet &as, PoseBatch &pb, int npose) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
   const int nwords = (as.ngroups + 31) / 32;
-  int gx = (as.n + 255) / 256;
-  if (gx > 64) gx = 64;
   prof_begin(PK_SETUP);
-  atom_box_kernel<<<dim3(gx, npose), 256, 0, c.stream>>>(pb.d_geom, as.n, pb.d_tpos, as.d_const, as.prm.invgs, pb.d_boxes);
-  VT_LAUNCHED();
+  int rc = lists_boxes_and_bins(as, pb, npose);
+  if (rc) return rc;
   gather_kernel<<<c.sm_count * 8, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, pb.d_bitmap, pb.tiles_cap, nwords,
                                                       pb.d_boxes, pb.d_tlist, pb.d_tcount, pb.cap_t, pb.d_totals + 2, pb.d_totals + 4);
   prof_end(PK_SETUP);
@@ -387,9 +448,10 @@ int batch_lists_back(const AtomSet &as, PoseBatch &pb, int npose) {
   Ctx &c = ctx();
   prof_begin(PK_SPLAT);
   // persistent: the warps draw their tasks from a queue, so one resident set of CTAs is enough (6 fit an SM).
-  // The fit pipeline asks for 4 per SM: the kernel saturates the shared-memory pipe long before it runs out
-  // of warps, and the free third of each SM is where the list building of the next batch runs beside it
-  // (measured 6 / 5 / 4 / 3 per SM: 35.0 / 35.5 / 36.9 / 33.2 k poses/s)
+  // The fit pipeline asks for 5 per SM: the kernel saturates the shared-memory pipe long before it runs out
+  // of warps, and the free slots are where the list building of the next batch runs beside it
+  // (measured 6 / 5 / 4 per SM: 38.3 / 38.6 / 37.6 k poses/s; with the heavier front end before the group
+  // boxes it was 35.0 / 35.5 / 36.9)
   static const int forced = getenv("VOLTOOL_SPLAT_CTAS") ? atoi(getenv("VOLTOOL_SPLAT_CTAS")) : 0;
   const int per_sm = forced > 0 ? forced : (pb.splat_ctas > 0 ? pb.splat_ctas : 6);
   splat_list_kernel<<<c.sm_count * per_sm, 128, 0, c.stream>>>(pb.d_geom, pb.d_totals, npose, as.n, pb.d_tpos, as.d_const,
