@@ -9,7 +9,7 @@
 //   gather_kernel     warp per tile: walk the tile's group bitmap, test the 32 boxes of each group,
 //                     append id | region-mask << 24 to the tile's list in global memory (L2 resident)
 //   splat_list_kernel warp per (tile, region): filter the list by region bit, stage 32 atoms at a
-//                     time as separable records, accumulate 8 x-voxels per thread, write once
+//                     time as separable records, accumulate 2 columns x 4 x-voxels per thread, write once
 //
 // A tile whose list would overflow its slot sets a flag; the caller then reruns the batch with the
 // cooperative kernel (no silent truncation).
@@ -235,7 +235,12 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
   const unsigned int lt = (1u << lane) - 1u;
   const long ntask = (long)totals[0] * kSplatWarps;
   int *queue = queues;
-  const int ly = lane & 7, lz = lane >> 3;
+  // lane = (x half, y, z pair): the lane evaluates the y-z factor of ONE column, (y, 2 zp + xh), and gets the
+  // factor of the neighbouring column (y, 2 zp + (xh ^ 1)) from its partner lane by shuffle; it accumulates
+  // its four x-voxels (half of Ex) for both columns.  A visit is then 6 shared-memory-pipe wavefronts (half of
+  // Ex: 2, dy^2, dz^2, the constants, the shuffle: 1 each) instead of 7 for the same 4 FFMA2 and one ex2 --
+  // the kernel saturates the shared-memory pipe, not the issue slots
+  const int ly = lane & 7, xh = (lane >> 3) & 1, zp = lane >> 4;
   float *rec = s_rec[warp];
   while (true) {
     // regions cost very different amounts (empty corners vs the dense interior): warps draw them from a queue
@@ -302,14 +307,14 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
       // branch-free: a staged atom whose disc misses every lane just adds zeros (rare: its box already
       // meets this region).  Two atoms per trip so their shared-memory loads overlap.
       auto visit = [&](const float *r) {
-        const float d2 = r[8 + ly] + r[16 + lz];                                  // dy*dy + dz*dz
+        const float d2 = r[8 + ly] + r[16 + 2 * zp + xh];                         // dy*dy + dz*dz of this lane's column
         const float2 c2 = *reinterpret_cast<const float2 *>(r + 20);              // arinv, radlim^2
         const float e = (d2 < c2.y) ? ex2_approx2(d2 * c2.x) : 0.0f;              // !(dy2dz2 >= radlim2)
-        const ulonglong2 e0 = *reinterpret_cast<const ulonglong2 *>(r);
-        const ulonglong2 e1 = *reinterpret_cast<const ulonglong2 *>(r + 4);
-        const f32x2 ee = pack2(e, e);
-        acc[0] = fma2(e0.x, ee, acc[0]); acc[1] = fma2(e0.y, ee, acc[1]);
-        acc[2] = fma2(e1.x, ee, acc[2]); acc[3] = fma2(e1.y, ee, acc[3]);
+        const float eo = __shfl_xor_sync(0xffffffffu, e, 8);                      // the partner's column
+        const ulonglong2 ex = *reinterpret_cast<const ulonglong2 *>(r + 4 * xh);  // Ex of this lane's four x
+        const f32x2 e2 = pack2(e, e), eo2 = pack2(eo, eo);
+        acc[0] = fma2(ex.x, e2, acc[0]); acc[1] = fma2(ex.y, e2, acc[1]);         // own column
+        acc[2] = fma2(ex.x, eo2, acc[2]); acc[3] = fma2(ex.y, eo2, acc[3]);       // partner's column
       };
       int a = 0;
       for (; a + 2 <= m; a += 2) {
@@ -344,15 +349,20 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
     }
     if (have > 0) process(have);
 
-    const int Y = Y0 + ly, Z = Z0 + lz;
-    if (Y < nv1 && Z < nv2) {
-      float *row = grid_all + (size_t)p * cap_grid + ((size_t)Z * nv1 + Y) * nv0;
+    const int Y = Y0 + ly;
+    if (Y < nv1) {
       float o[8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) unpack2(acc[k], o[2 * k], o[2 * k + 1]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (X0 + k < nv0) row[X0 + k] = o[k];
+      for (int c = 0; c < 2; ++c) {
+        const int Z = Z0 + 2 * zp + (c == 0 ? xh : (xh ^ 1));   // own column, then the partner's
+        if (Z >= nv2) continue;
+        float *row = grid_all + (size_t)p * cap_grid + ((size_t)Z * nv1 + Y) * nv0 + X0 + 4 * xh;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (X0 + 4 * xh + k < nv0) row[k] = o[4 * c + k];
+      }
     }
   }
 }
