@@ -31,7 +31,9 @@ for it in range(N):
             for k in ("VOLTOOL_CC_STAGED", "VOLTOOL_CC_IDENTITY", "VOLTOOL_FORCE_GENERIC"): os.environ.pop(k, None)
             os.environ.update(env)
             got, ng, _ = vt.cc_threaded(vt.VolMap(GA, a), vt.VolMap(GB, b), thr, full=True)
-            same = (np.isnan(want) and np.isnan(got)) or abs(got - want) <= 1e-9
+            # the ring and identity kernels add the five sums in float over 4 rows before the double sum
+            tol = 2e-7 if env and "GENERIC" not in next(iter(env)) else 1e-9
+            same = (np.isnan(want) and np.isnan(got)) or abs(got - want) <= tol
             if ng != nw or not same:
                 bad += 1; print("CC MISMATCH", sa, sb, spa, spb, thr, env, got, want, ng, nw, flush=True)
     for k in ("VOLTOOL_CC_STAGED", "VOLTOOL_CC_IDENTITY", "VOLTOOL_FORCE_GENERIC"): os.environ.pop(k, None)
