@@ -334,8 +334,11 @@ def run_ours(args):
         vt.sync()
         t0 = time.perf_counter()
         p_fit, fres = vt.fit(pos, radii, mass, tmap, RESOLUTION)
+        dt_first = time.perf_counter() - t0     # includes growing the stream-ordered memory pool by the call's ~1 GB workspace
+        t0 = time.perf_counter()
+        p_fit, fres = vt.fit(pos, radii, mass, tmap, RESOLUTION)
         dt = time.perf_counter() - t0
-        out["fit_call"] = {"seconds": dt, "candidates_computed": int(fres.n_computed),
+        out["fit_call"] = {"seconds": dt, "first_call_seconds": dt_first, "candidates_computed": int(fres.n_computed),
                            "candidates_visited_by_reference_loop": int(fres.n_evaluated), "best_cc": float(fres.best_cc),
                            "stage_best": list(fres.stage_best), "note": "vt_fit incl. vol_com on the 256^3 target"}
     if world == 1:
