@@ -1,5 +1,5 @@
 // vt_splat2.cu -- barrier-free splat: per-tile atom lists (one warp per tile) + per-region
-// accumulation (one warp per 8x8x4 region).  Same arithmetic and the same deterministic
+// accumulation (one warp per 8x8x8 region).  Same arithmetic and the same deterministic
 // accumulation order per voxel as the cooperative kernel in vt_sim.cu up to how partial sums are grouped
 // (group order, then lane order; the two agree to a few 1e-7 relative, tests/test_gpu_fullsize.py), but no
 // block barrier anywhere, so unevenly filled regions do not stall one another:
@@ -9,7 +9,7 @@
 //   gather_kernel     warp per tile: walk the tile's group bitmap, test the 32 boxes of each group,
 //                     append id | region-mask << 24 to the tile's list in global memory (L2 resident)
 //   splat_list_kernel warp per (tile, region): filter the list by region bit, stage 32 atoms at a
-//                     time as separable records, accumulate 2 columns x 4 x-voxels per thread, write once
+//                     time as separable records, accumulate 4 columns x 4 x-voxels per thread, write once
 //
 // A tile whose list would overflow its slot sets a flag; the caller then reruns the batch with the
 // cooperative kernel (no silent truncation).
@@ -35,6 +35,8 @@ __device__ __forceinline__ int find_pose_tile(const PoseGeom *__restrict__ geo, 
   }
   return lo;
 }
+
+constexpr int kListRegions = 4;   // regions of the list path: 8 x 8 x 8 voxels, 2 x 2 x 1 per tile (bit r: x half r&1, y half r>>1)
 
 // ------------------------------------------------------------------------------------------ boxes
 __global__ void __launch_bounds__(256) atom_box_kernel(const PoseGeom *__restrict__ geo, int natoms,
@@ -193,13 +195,12 @@ __global__ void __launch_bounds__(128) gather_kernel(const PoseGeom *__restrict_
                           ymax >= y0 && zmin <= z0 + kTZ - 1 && zmax >= z0;
         int mask = 0;
         if (take) {
-          // bit w: box meets region w (x half w&1, z half (w>>1)&1, y block w>>2): the AND of three
-          // byte patterns, one per axis, each the OR of the halves the box reaches
-          static_assert(kSplatWarps == 8, "region masks are written for 2 x 2 x 2 regions per tile");
-          const int bx_ = (xmin <= x0 + 7 ? 0x55 : 0) | (xmax >= x0 + 8 ? 0xaa : 0);
-          const int bz_ = (zmin <= z0 + 3 ? 0x33 : 0) | (zmax >= z0 + 4 ? 0xcc : 0);
-          const int by_ = (ymin <= y0 + 7 ? 0x0f : 0) | (ymax >= y0 + 8 ? 0xf0 : 0);
-          mask = bx_ & bz_ & by_;
+          // bit r: box meets region r (x half r&1, y half r>>1; a region spans the tile in z): the AND of two
+          // nibble patterns, one per axis, each the OR of the halves the box reaches
+          static_assert(kListRegions == 4 && kTX == 16 && kTY == 16, "region masks are written for 2 x 2 x 1 regions per tile");
+          const int bx_ = (xmin <= x0 + 7 ? 0x5 : 0) | (xmax >= x0 + 8 ? 0xa : 0);
+          const int by_ = (ymin <= y0 + 7 ? 0x3 : 0) | (ymax >= y0 + 8 ? 0xc : 0);
+          mask = bx_ & by_;
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, take);
         if (take) {
@@ -218,9 +219,9 @@ __global__ void __launch_bounds__(128) gather_kernel(const PoseGeom *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------ accumulate
-constexpr int kRec2 = 28;  // Ex[8] | dy^2[8] | dz^2[4] | arinv, radlim^2, pad x 6 (stride 28: the 16-byte staging stores of 8 lanes cover all 32 banks)
+constexpr int kRec2 = 28;  // Ex[8] | dy^2[8] | dz^2[8] | arinv, radlim^2, pad x 2 (stride 28: the 16-byte staging stores of 8 lanes cover all 32 banks)
 
-__global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__restrict__ geo,
+__global__ void __launch_bounds__(128, 5) splat_list_kernel(const PoseGeom *__restrict__ geo,
                                                             const int *__restrict__ totals, int npose, int natoms,
                                                             const float4 *__restrict__ tpos_all,
                                                             const float4 *__restrict__ cst,
@@ -233,14 +234,15 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
   __shared__ int s_pend[4][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int lt = (1u << lane) - 1u;
-  const long ntask = (long)totals[0] * kSplatWarps;
+  const long ntask = (long)totals[0] * kListRegions;
   int *queue = queues;
-  // lane = (x half, y, z pair): the lane evaluates the y-z factor of ONE column, (y, 2 zp + xh), and gets the
-  // factor of the neighbouring column (y, 2 zp + (xh ^ 1)) from its partner lane by shuffle; it accumulates
-  // its four x-voxels (half of Ex) for both columns.  A visit is then 6 shared-memory-pipe wavefronts (half of
-  // Ex: 2, dy^2, dz^2, the constants, the shuffle: 1 each) instead of 7 for the same 4 FFMA2 and one ex2 --
-  // the kernel saturates the shared-memory pipe, not the issue slots
-  const int ly = lane & 7, xh = (lane >> 3) & 1, zp = lane >> 4;
+  // A warp owns one 8 x 8 x 8 region; lane = (x half, y, z quad) owns 4 x-voxels of the four columns (y, 4 zq + c).
+  // It evaluates the y-z factor of two of them, (y, 4 zq + 2 xh + {0, 1}), and takes the other two from its
+  // partner lane (same y and z quad, other x half) by shuffle.  A visit is 7 shared-memory-pipe wavefronts (half
+  // of Ex: 2; dy^2, the dz^2 pair, the constants: 1 each; two shuffles) for 16 voxels and 8 FFMA2 -- half the
+  // wavefronts per voxel of the 8 x 8 x 4 regions this replaced, which is what counts: the kernel saturates the
+  // shared-memory pipe, not the issue slots.  A region twice as tall also meets a third fewer atoms per voxel.
+  const int ly = lane & 7, xh = (lane >> 3) & 1, zq = lane >> 4;
   float *rec = s_rec[warp];
   while (true) {
     // regions cost very different amounts (empty corners vs the dense interior): warps draw them from a queue
@@ -248,22 +250,22 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
     if (lane == 0) task = atomicAdd(queue, 1);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= ntask) break;
-    const int item = (int)(task / kSplatWarps), region = (int)(task - (long)item * kSplatWarps);
+    const int item = (int)(task / kListRegions), region = (int)(task - (long)item * kListRegions);
     const int p = find_pose_tile(geo, npose, item);
     const PoseGeom &G = geo[p];
     const int local = item - G.tile_base;
     const int tx = local % G.tiles[0], ty = (local / G.tiles[0]) % G.tiles[1], tz = local / (G.tiles[0] * G.tiles[1]);
     const int nv0 = G.nv[0], nv1 = G.nv[1], nv2 = G.nv[2];
     const float ox = G.org[0], oy = G.org[1], oz = G.org[2];
-    const int X0 = tx * kTX + (region & 1) * 8, Y0 = ty * kTY + (region >> 2) * 8, Z0 = tz * kTZ + ((region >> 1) & 1) * 4;
+    const int X0 = tx * kTX + (region & 1) * 8, Y0 = ty * kTY + (region >> 1) * 8, Z0 = tz * kTZ;
     const float4 *__restrict__ tpos = tpos_all + (size_t)p * natoms;
     const uint3 *__restrict__ bx = boxes + (size_t)p * natoms;
     const unsigned int *__restrict__ list = tlist + ((size_t)p * tiles_cap + local) * cap_t;
     const int n = min(tcount[(size_t)p * tiles_cap + local], cap_t);
 
-    f32x2 acc[4];  // 8 consecutive x as four packed pairs
+    f32x2 acc[8];  // [column c][x pair]: c = 0, 1 own columns (z = 4 zq + 2 xh + c), c = 2, 3 the partner's
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = pack2(0.0f, 0.0f);
+    for (int k = 0; k < 8; ++k) acc[k] = pack2(0.0f, 0.0f);
 
     auto process = [&](int m) {
       if (lane < m) {
@@ -295,26 +297,33 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
         *reinterpret_cast<float4 *>(r + 8) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4 *>(r + 12) = make_float4(v[4], v[5], v[6], v[7]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 8; ++k) {
           const int Z = Z0 + k;
           const float dz = (float)Z * gs - az;
           v[k] = (Z >= zmin && Z <= zmax) ? dz * dz : INFINITY;
         }
         *reinterpret_cast<float4 *>(r + 16) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(r + 20) = make_float4(arinv, k4.y, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(r + 20) = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<float4 *>(r + 24) = make_float4(arinv, k4.y, 0.f, 0.f);
       }
       __syncwarp();
       // branch-free: a staged atom whose disc misses every lane just adds zeros (rare: its box already
       // meets this region).  Two atoms per trip so their shared-memory loads overlap.
       auto visit = [&](const float *r) {
-        const float d2 = r[8 + ly] + r[16 + 2 * zp + xh];                         // dy*dy + dz*dz of this lane's column
-        const float2 c2 = *reinterpret_cast<const float2 *>(r + 20);              // arinv, radlim^2
-        const float e = (d2 < c2.y) ? ex2_approx2(d2 * c2.x) : 0.0f;              // !(dy2dz2 >= radlim2)
-        const float eo = __shfl_xor_sync(0xffffffffu, e, 8);                      // the partner's column
-        const ulonglong2 ex = *reinterpret_cast<const ulonglong2 *>(r + 4 * xh);  // Ex of this lane's four x
-        const f32x2 e2 = pack2(e, e), eo2 = pack2(eo, eo);
-        acc[0] = fma2(ex.x, e2, acc[0]); acc[1] = fma2(ex.y, e2, acc[1]);         // own column
-        acc[2] = fma2(ex.x, eo2, acc[2]); acc[3] = fma2(ex.y, eo2, acc[3]);       // partner's column
+        const float dy2 = r[8 + ly];
+        const float2 dz2 = *reinterpret_cast<const float2 *>(r + 16 + 4 * zq + 2 * xh);   // this lane's two columns
+        const float2 c2 = *reinterpret_cast<const float2 *>(r + 24);                      // arinv, radlim^2
+        const float d2a = dy2 + dz2.x, d2b = dy2 + dz2.y;                                 // dy*dy + dz*dz
+        const float ea = (d2a < c2.y) ? ex2_approx2(d2a * c2.x) : 0.0f;                   // !(dy2dz2 >= radlim2)
+        const float eb = (d2b < c2.y) ? ex2_approx2(d2b * c2.x) : 0.0f;
+        const float ec = __shfl_xor_sync(0xffffffffu, ea, 8);                             // the partner's two columns
+        const float ed = __shfl_xor_sync(0xffffffffu, eb, 8);
+        const ulonglong2 ex = *reinterpret_cast<const ulonglong2 *>(r + 4 * xh);          // Ex of this lane's four x
+        const f32x2 a2 = pack2(ea, ea), b2 = pack2(eb, eb), c22 = pack2(ec, ec), d22 = pack2(ed, ed);
+        acc[0] = fma2(ex.x, a2, acc[0]); acc[1] = fma2(ex.y, a2, acc[1]);
+        acc[2] = fma2(ex.x, b2, acc[2]); acc[3] = fma2(ex.y, b2, acc[3]);
+        acc[4] = fma2(ex.x, c22, acc[4]); acc[5] = fma2(ex.y, c22, acc[5]);
+        acc[6] = fma2(ex.x, d22, acc[6]); acc[7] = fma2(ex.y, d22, acc[7]);
       };
       int a = 0;
       for (; a + 2 <= m; a += 2) {
@@ -351,17 +360,18 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
 
     const int Y = Y0 + ly;
     if (Y < nv1) {
-      float o[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) unpack2(acc[k], o[2 * k], o[2 * k + 1]);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int Z = Z0 + 2 * zp + (c == 0 ? xh : (xh ^ 1));   // own column, then the partner's
+      for (int c = 0; c < 4; ++c) {
+        // acc[2c], acc[2c+1]: c < 2 own columns, else the partner's
+        const int Z = Z0 + 4 * zq + 2 * (c < 2 ? xh : (xh ^ 1)) + (c & 1);
         if (Z >= nv2) continue;
+        float o[4];
+        unpack2(acc[2 * c], o[0], o[1]);
+        unpack2(acc[2 * c + 1], o[2], o[3]);
         float *row = grid_all + (size_t)p * cap_grid + ((size_t)Z * nv1 + Y) * nv0 + X0 + 4 * xh;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (X0 + 4 * xh + k < nv0) row[k] = o[4 * c + k];
+          if (X0 + 4 * xh + k < nv0) row[k] = o[k];
       }
     }
   }
