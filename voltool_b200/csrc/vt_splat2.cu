@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128) gather_kernel(const PoseGeom *__restrict_
 // ------------------------------------------------------------------------------------------ accumulate
 constexpr int kRec2 = 28;  // Ex[8] | dy^2[8] | dz^2[8] | arinv, radlim^2, pad x 2 (stride 28: the 16-byte staging stores of 8 lanes cover all 32 banks)
 
-__global__ void __launch_bounds__(128, 5) splat_list_kernel(const PoseGeom *__restrict__ geo,
+__global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__restrict__ geo,
                                                             const int *__restrict__ totals, int npose, int natoms,
                                                             const float4 *__restrict__ tpos_all,
                                                             const float4 *__restrict__ cst,
