@@ -326,11 +326,13 @@ __global__ void __launch_bounds__(128, 6) splat_list_kernel(const PoseGeom *__re
         acc[6] = fma2(ex.x, d22, acc[6]); acc[7] = fma2(ex.y, d22, acc[7]);
       };
       int a = 0;
-      for (; a + 2 <= m; a += 2) {
+      for (; a + 4 <= m; a += 4) {
         visit(rec + a * kRec2);
         visit(rec + (a + 1) * kRec2);
+        visit(rec + (a + 2) * kRec2);
+        visit(rec + (a + 3) * kRec2);
       }
-      if (a < m) visit(rec + a * kRec2);
+      for (; a < m; ++a) visit(rec + a * kRec2);
       __syncwarp();
     };
 
