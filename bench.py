@@ -304,11 +304,11 @@ def run_ours(args):
     roofline = {"kernel": "splat_list_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": (achieved / fp32_peak) if achieved else None,
                 "traffic": 5.15e8 * (splat_n and (P * K / splat_n) / 128.0) if args.atoms == 50000 else None,
-                "traffic_source": "profiles/r1c_splat_list_kernel_summary.txt: dram read 287 MB + write 228 MB per 128-pose launch",
+                "traffic_source": "profiles/r1k_splat_list_kernel_summary.txt: dram read 285 MB + write 230 MB per 128 poses",
                 "peak_source": f"{props['sm_count']} SMs x 128 lanes x 2 x sm_max_mhz ({peaks['source']} MEASURED_PEAKS); "
                                "no tensor cores: nothing here is a contraction",
-                "binding_resource": "shared-memory pipe, then instruction issue (ncu of this kernel alone: l1tex 84 % busy, "
-                                    "issue 59 %; profiles/r1g_splat_list_kernel_summary.txt); only ~1 in 8 (atom, voxel) "
+                "binding_resource": "shared-memory pipe, then instruction issue (ncu of this kernel alone: l1tex 71 % busy, "
+                                    "issue 71 %; profiles/r1k_splat_list_kernel_summary.txt); only ~1 in 7 (atom, voxel) "
                                     "evaluations of a warp lands inside the atom's cutoff box, which is what `frac` shows",
                 "pairs_per_pose": pairs, "flop_per_pair": FLOP_PER_PAIR,
                 "ms_per_launch": splat_ms / max(splat_n, 1), "launches": splat_n,
