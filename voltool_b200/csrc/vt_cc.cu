@@ -223,7 +223,7 @@ static bool identity_tables(const std::vector<AxisEntry> &tab, const int off[6],
 
 constexpr int kZChunk = 32;  // output z steps per warp work item
 
-__global__ void __launch_bounds__(kThreads, 2) cc_sep_kernel(DevMap A, DevMap B, int nx, int ny, int nz,
+__global__ void __launch_bounds__(kThreads, 2) cc_sep_kernel(DevMap A, DevMap B, int nx, int ny, int nz, int zchunk,
                                                           const AxisEntry *__restrict__ T, int offAx, int offAy,
                                                           int offAz, int offBx, int offBy, int offBz, float thr_f,
                                                           double *partials, unsigned int *ticket, double *out) {
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 2) cc_sep_kernel(DevMap A, DevMap B,
   // work item = (32-wide x tile, kRows y rows, z chunk), dealt to warps round-robin (x tile fastest)
   const int xtiles = (nx + 31) >> 5;
   const int ygroups = (ny + kRows - 1) / kRows;
-  const int zchunks = (nz + kZChunk - 1) / kZChunk;
+  const int zchunks = (nz + zchunk - 1) / zchunk;
   const long work = (long)xtiles * ygroups * zchunks;
   const int lane = threadIdx.x & 31;
   const long wstride = (long)gridDim.x * (kThreads / 32);
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 2) cc_sep_kernel(DevMap A, DevMap B,
     const long r = w / xtiles;
     const int yg = (int)(r % ygroups), zc = (int)(r / ygroups);
     cc_march_item<kRows>(A.d, A.nx, A.ny, B.d, B.nx, B.ny, T + offAx, T + offAy, T + offAz, T + offBx, T + offBy, T + offBz, nx,
-                  ny, xb * 32 + lane, yg * kRows, zc * kZChunk, min(nz, (zc + 1) * kZChunk), thr_f, a);
+                  ny, xb * 32 + lane, yg * kRows, zc * zchunk, min(nz, (zc + 1) * zchunk), thr_f, a);
   }
   double acc[6] = {a.s[0], a.s[1], a.s[2], a.s[3], a.s[4], (double)a.n};
   block_sum<6>(acc, sm);
@@ -323,11 +323,16 @@ int k_cc(const vt_map *A, const vt_map *B, double thr, double sums[5], long *n) 
                        c.d_ticket, dout);
     if (st > 1) return st;
     if (st == 1) {
-      const long work = (long)((og.xsize + 31) / 32) * ((og.ysize + kRows - 1) / kRows) * ((og.zsize + kZChunk - 1) / kZChunk);
+      // z steps per warp work item: 32, shorter for small maps so that there are enough items to fill the GPU
+      // (a 128^3 intersection has 512 items of 32 x 4 x 32 voxels for 2368 resident warps)
+      int zchunk = kZChunk;
+      const long xy_items = (long)((og.xsize + 31) / 32) * ((og.ysize + kRows - 1) / kRows);
+      while (zchunk > 4 && xy_items * ((og.zsize + zchunk - 1) / zchunk) < (long)c.sm_count * 2 * (kThreads / 32)) zchunk /= 2;
+      const long work = xy_items * ((og.zsize + zchunk - 1) / zchunk);
       const long wblocks = (work + kThreads / 32 - 1) / (kThreads / 32);
       int grid = (int)(wblocks < (long)c.sm_count * 8 ? wblocks : (long)c.sm_count * 8);
       prof_begin(PK_CC);
-      cc_sep_kernel<<<grid, kThreads, 0, c.stream>>>(dA, dB, og.xsize, og.ysize, og.zsize, T.d, T.offAx, T.offAy, T.offAz,
+      cc_sep_kernel<<<grid, kThreads, 0, c.stream>>>(dA, dB, og.xsize, og.ysize, og.zsize, zchunk, T.d, T.offAx, T.offAy, T.offAz,
                                                      T.offBx, T.offBy, T.offBz, threshold_as_float(thr), partials, c.d_ticket, dout);
       prof_end(PK_CC);
       VT_LAUNCHED();
