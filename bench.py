@@ -148,13 +148,34 @@ def splat_pairs(radii, radscale, gspacing, gausslim=4.0):
     return float(np.sum(b ** 3))
 
 
+def build_cfg2(vt, atoms, n):
+    """BASELINE configs[1] on the device: `atoms` atoms in a ball, target = 1 A density of the structure in the
+    PLANTED pose, zero-padded to n^3, + N(0, 0.02 max) noise; the structure is then COM-aligned to the map as
+    fit() does (TclVoltool.C:789-803).  Returns pos, radii, mass, com, resident target map."""
+    from voltool_b200.synth import make_structure, add_noise
+    pos, radii, mass = make_structure(atoms, 52.0 * (atoms / 50000.0) ** (1 / 3), seed=2001, center=(0.5 * (n - 1),) * 3)
+    com0 = vt.measure_center(pos, mass)
+    planted = vt.pose_apply(pos, com0, PLANTED)
+    radscale, gsp, quality = vt.sim_policy(RESOLUTION)
+    tmap = vt.sim(planted, radii, quality, radscale, 1.0)      # 1 A sampling of the planted pose
+    g = tmap.grid
+    padm = [(n - s) // 2 for s in (g.xsize, g.ysize, g.zsize)]
+    padp = [n - s - m for s, m in zip((g.xsize, g.ysize, g.zsize), padm)]
+    tmap.pad(padm[0], padp[0], padm[1], padp[1], padm[2], padp[2])
+    tmap.upload(add_noise(tmap.data, 0.02, seed=2002))
+    tg = tmap.grid
+    assert (tg.xsize, tg.ysize, tg.zsize) == (n, n, n)
+    dencom = tmap.vol_com()
+    pos = (pos + (dencom - com0)[None, :]).astype(np.float32)   # fit's COM alignment (TclVoltool.C:800)
+    com = vt.measure_center(pos, mass)
+    return pos, radii, mass, com, tmap
+
+
 # ================================================================================================ ours
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import voltool_b200 as vt
-    from voltool_b200.synth import make_structure, add_noise
-
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -178,28 +199,17 @@ def run_ours(args):
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
     vt.init(local)
+    if world > 1:
+        from voltool_b200 import dist as vdist
+        vdist.init_nccl_from_torch()      # the LIBRARY's communicator: the path's one collective is issued by the library
     props = vt.device_props()
     stream = torch.cuda.ExternalStream(vt.lib().vt_stream(), device=torch.device("cuda", local))
     peaks = load_peaks()
 
     # ---- workload (every rank holds the full target map and atom set) ----
     n = args.map
-    pos, radii, mass = make_structure(args.atoms, 52.0 * (args.atoms / 50000.0) ** (1 / 3), seed=2001,
-                                      center=(0.5 * (n - 1),) * 3)
-    com0 = vt.measure_center(pos, mass)
-    planted = vt.pose_apply(pos, com0, PLANTED)
+    pos, radii, mass, com, tmap = build_cfg2(vt, args.atoms, n)
     radscale, gsp, quality = vt.sim_policy(RESOLUTION)
-    tmap = vt.sim(planted, radii, quality, radscale, 1.0)      # 1 A sampling of the planted pose
-    g = tmap.grid
-    padm = [(n - s) // 2 for s in (g.xsize, g.ysize, g.zsize)]
-    padp = [n - s - m for s, m in zip((g.xsize, g.ysize, g.zsize), padm)]
-    tmap.pad(padm[0], padp[0], padm[1], padp[1], padm[2], padp[2])
-    tmap.upload(add_noise(tmap.data, 0.02, seed=2002))
-    tg = tmap.grid
-    assert (tg.xsize, tg.ysize, tg.zsize) == (n, n, n)
-    dencom = tmap.vol_com()
-    pos = (pos + (dencom - com0)[None, :]).astype(np.float32)   # fit's COM alignment (TclVoltool.C:800)
-    com = vt.measure_center(pos, mass)
     ctx = vt.FitContext(pos, radii, tmap, RESOLUTION)
 
     poses = pose_list()
@@ -218,16 +228,13 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def step_resident(s):
+        # all three on the library stream: pose pipeline, per-shard best (cc, pose index), ONE small ncclAllGather
         ctx.eval_poses_device(com, dev_poses[s].data_ptr(), P, d_cc.data_ptr())
-        with torch.cuda.stream(stream):
-            v, i = torch.max(torch.nan_to_num(d_cc, nan=-2.0), 0)
-            best_local[0], best_local[1] = v, i.to(torch.float32)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, best_local)   # the one collective of the path
-            else:
-                gathered.copy_(best_local)
+        vt.best_pose_device(d_cc.data_ptr(), P, ((s * world + rank) * P) % len(poses), best_local.data_ptr())
+        vt.nccl_allgather(best_local.data_ptr(), gathered.data_ptr(), 2)
 
     def barrier():
+        vt.sync()                      # the library stream first: its collective never overlaps torch's barrier
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -261,7 +268,7 @@ def run_ours(args):
         sampler.start()
     ms_total = timed(step_resident, W, K)
     clocks = sampler.stop() if rank == 0 else None
-    launches = vt.launch_count() - launches0 + 2 * K   # + torch max / copy per step
+    launches = vt.launch_count() - launches0           # every kernel of the step is the library's (the gather is NCCL's)
     prof = {k: vt.profile_get(k) for k in ("transform", "setup", "splat", "pose_cc")}
     vt.profile_enable(False)
     value = world * P * K / (ms_total * 1e-3)
@@ -271,15 +278,18 @@ def run_ours(args):
     host_slices = [slice_for(s) for s in range(W + K)]
     pinned = torch.from_numpy(pos.copy()).pin_memory()
 
+    mine = torch.empty(2, dtype=torch.float32, device="cuda")
+    mine_host = torch.empty(2, dtype=torch.float32).pin_memory()
+
     def step_e2e(s):
         ctx.set_origin(pinned.numpy())                       # H2D: 3*natoms floats (+ group spheres)
         cc = ctx.eval_poses(com, host_slices[s])             # H2D: pose list; D2H: cc per pose
         i = int(np.nanargmax(cc))
-        mine = torch.tensor([float(cc[i]), float(i)], device="cuda")
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, mine)
-        else:
-            gathered.copy_(mine)
+        mine_host[0], mine_host[1] = float(cc[i]), float(((s * world + rank) * P) % len(poses) + i)
+        with torch.cuda.stream(stream):
+            mine.copy_(mine_host, non_blocking=True)
+        vt.nccl_allgather(mine.data_ptr(), gathered.data_ptr(), 2)
+        vt.sync()
         return float(gathered[0].item())                     # D2H read of the merged result
 
     step_e2e(0)
@@ -290,8 +300,44 @@ def run_ours(args):
     h2d = args.atoms * 16 + (args.atoms + 31) // 32 * 16 + P * 36
     d2h = P * 4 + 4
 
+    # ---- strong scaling of ONE `voltool fit` (the reference's own 5-stage schedule, TclVoltool.C:895-909): every rank
+    # calls vt_fit on the same inputs; the library shards each rotate() table (rank r: candidates r, r + N, ...), merges it
+    # with one ncclAllGather on device buffers per stage and replays the skip rule identically on every rank
+    fit_sharded = None
+    if not args.no_extras:
+        vt.fit(pos, radii, mass, tmap, RESOLUTION)           # warm-up: grows the memory pool by the workspace
+        reps, times, dev_ms = 3, [], []
+        for _ in range(reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record()
+            t0 = time.perf_counter()
+            p_fit, fres = vt.fit(pos, radii, mass, tmap, RESOLUTION)
+            with torch.cuda.stream(stream):
+                e1.record()
+            vt.sync()
+            times.append(time.perf_counter() - t0)
+            dev_ms.append(e0.elapsed_time(e1))
+        tt = torch.tensor([min(times), min(dev_ms)], device="cuda", dtype=torch.float64)
+        sig = torch.tensor([float(np.float64(p_fit.astype(np.float64).sum())), float(fres.best_cc)], device="cuda", dtype=torch.float64)
+        sig_all = [torch.zeros_like(sig) for _ in range(world)]
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_gather(sig_all, sig)
+        else:
+            sig_all = [sig]
+        same = all(bool(torch.equal(x, sig_all[0])) for x in sig_all)
+        fit_sharded = {"seconds": float(tt[0].item()), "device_ms": float(tt[1].item()), "ranks": world,
+                       "candidates_computed": int(fres.n_computed), "candidates_visited_by_reference_loop": int(fres.n_evaluated),
+                       "best_cc": float(fres.best_cc), "stage_best": list(fres.stage_best), "all_ranks_same_pose": same,
+                       "collective": "ncclAllGather of the per-rank CC slices on device buffers, one per rotate() table (5 per fit)"
+                                     if world > 1 else "none (one rank)",
+                       "note": "whole vt_fit call incl. vol_com of the 256^3 target and the workspace set-up; max over ranks, best of 3"}
+
     if rank != 0:
         if world > 1:
+            vt.nccl_shutdown()
             dist.destroy_process_group()
         return
 
@@ -321,29 +367,33 @@ def run_ours(args):
                       "atoms": args.atoms, "map": [n, n, n], "resolution": RESOLUTION, "poses_per_step_per_gpu": P,
                       "pose_list": "25x20x20 Euler lattice x 3x3x3 shifts (270000), permuted, sliced per rank",
                       "l2": "per-step working set (target 64 MiB + per-pose grids/coordinates, several GB) exceeds the 126 MB L2",
-                      "parallelism": f"pose-shard x{world}, one all_gather of (cc, index) per step"},
+                      "parallelism": f"pose-shard x{world}, one ncclAllGather of (cc, index) per step issued by the library"},
            "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": ms_e2e / K, "wall_s": wall_e2e},
            "gpu_launches": int(launches), "roofline": roofline,
            "best_of_last_step": {"cc": float(best[:, 0].max()), "planted_deg": PLANTED}}
 
-    if world == 1 and not args.no_extras:
-        # the reference's own workload: one full `voltool fit` (COM alignment, 3375 + 432 + 128 candidates,
-        # skip-rule replay) through the C ABI with host buffers
-        vt.sync()
-        t0 = time.perf_counter()
-        p_fit, fres = vt.fit(pos, radii, mass, tmap, RESOLUTION)
-        dt_first = time.perf_counter() - t0     # includes growing the stream-ordered memory pool by the call's ~1 GB workspace
-        t0 = time.perf_counter()
-        p_fit, fres = vt.fit(pos, radii, mass, tmap, RESOLUTION)
-        dt = time.perf_counter() - t0
-        out["fit_call"] = {"seconds": dt, "first_call_seconds": dt_first, "candidates_computed": int(fres.n_computed),
-                           "candidates_visited_by_reference_loop": int(fres.n_evaluated), "best_cc": float(fres.best_cc),
-                           "stage_best": list(fres.stage_best), "note": "vt_fit incl. vol_com on the 256^3 target"}
+    if fit_sharded is not None:
+        out["fit_call"] = fit_sharded
     if world == 1:
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(pos, radii, com, tmap, poses, budget_s=args.cpu_budget)
+            # parity of the benchmarked path: the poses the CPU reference arm just scored, scored again through the
+            # timed entry point (device pose list -> vt_fit_eval_poses_device) and through the host-list entry point
+            ref_cc = np.asarray(out["cpu_baseline"].pop("_ccs"), np.float64)
+            m = len(ref_cc)
+            d_p = torch.from_numpy(np.ascontiguousarray(poses[:m])).cuda()
+            d_c = torch.empty(m, dtype=torch.float32, device="cuda")
+            ctx.eval_poses_device(com, d_p.data_ptr(), m, d_c.data_ptr())
+            vt.sync()
+            got_dev = d_c.cpu().numpy().astype(np.float64)
+            got_host = ctx.eval_poses(com, poses[:m]).astype(np.float64)
+            rel = np.abs(got_dev - ref_cc) / np.maximum(np.abs(ref_cc), 1e-30)
+            out["parity"] = {"n": int(m), "max_rel_err": float(rel.max()), "tol": 1e-5, "ok": bool(rel.max() <= 1e-5),
+                             "device_list_equals_host_list_bits": bool(np.array_equal(got_dev, got_host)),
+                             "against": "cpu_baseline's CC of the same poses (pose list entries incl. +-1 A shifts)",
+                             "cc_gpu_first": float(got_dev[0]), "cc_cpu_first": float(ref_cc[0])}
         if not args.no_extras:
             out["ops"] = extra_ops(vt, peaks, args)
             if args.cfg4_map > 0:
@@ -362,6 +412,7 @@ def run_ours(args):
                 out["cfg5"] = cfg5_leg(vt, args.cfg5_atoms, args.cfg5_edge)
     print(json.dumps(out))
     if world > 1:
+        vt.nccl_shutdown()
         dist.destroy_process_group()
 
 
@@ -381,7 +432,7 @@ def extra_ops(vt, peaks, args):
         vt.profile_reset(); vt.profile_enable(True)
         for _ in range(reps):
             fn()
-        ms, cnt = vt.profile_get(key)
+        ms = sum(vt.profile_get(k)[0] for k in key.split("+"))
         vt.profile_enable(False)
         return ms / reps
 
@@ -412,8 +463,13 @@ def extra_ops(vt, peaks, args):
     res["sadd"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8}
     ms = timeit("unary", lambda: A.clone().binmask(0.5))
     res["binmask"] = {"ms": ms, "GB/s": 8.0 * g.n / (ms * 1e-3) / 1e9, "bytes_per_voxel": 8}
-    ms = timeit("stats", lambda: (A.scalar_add(0.0), A.sigma()))   # sadd invalidates mean+sigma -> 2 passes
-    res["sigma"] = {"ms": ms, "GB/s": 8.0 * g.n / (ms * 1e-3) / 1e9, "bytes_per_voxel": 8, "note": "mean pass + sigma pass"}
+    # `voltool sigma` = VolumetricData::sigma_scale (TclVoltool.C:2167): mean pass + sigma pass + scale pass = 16 B/voxel
+    Sg = A.clone()
+    ms = timeit("stats+unary", lambda: Sg.sigma_scale())
+    gbs = 16.0 * g.n / (ms * 1e-3) / 1e9
+    res["sigma"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 16,
+                    "note": "sigma_scale: mean pass (4 B) + sigma pass (4 B) + scale pass (8 B)"}
+    del Sg
     C = A.clone()
     ms = timeit("blur", lambda: C.gaussian_blur(2.0), reps=3)
     gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
@@ -440,44 +496,65 @@ def extra_ops(vt, peaks, args):
         res["supersample"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_input_voxel": 36,
                               "out": [2 * n - 1] * 3}
     del A, B, C
-    # cfg1: sim + cc, 10k atoms, res 5, 1 A spacing
-    from voltool_b200.synth import make_structure
+    res["sim_cc_cfg1"] = cfg1_leg(vt, args)
+    return res
+
+
+def cfg1_leg(vt, args):
+    """BASELINE configs[0] as SURVEY 8d states it: 10 000 atoms (seed 1001, ball R = 30 A), -res 5 -spacing 1.0; the cc
+    target is that sim + N(0, 0.05 max) noise (seed 1002) on the identical grid; thresholds -FLT_MAX and 0.1.
+    One call = vt_sim_cc with host coordinates (atom sort + upload + splat + cc + readback).  Unit: voxels of the
+    simulated map per second."""
+    from voltool_b200.synth import make_structure, add_noise
+    FLT_MAX = 3.4028234663852886e38
     pos, radii, _ = make_structure(10000, 30.0, seed=1001)
     radscale, _, quality = vt.sim_policy(5.0, 1.0)
     S = vt.sim(pos, radii, quality, radscale, 1.0)
-    t0 = time.perf_counter()
+    sim = S.data
+    T = vt.VolMap(S.grid, add_noise(sim, 0.05, seed=1002))
+    nvox = S.gridsize()
+    out = {"voxels": nvox, "atoms": 10000, "target": "sim + N(0, 0.05 max), seed 1002, identical grid",
+           "note": "vt_sim_cc through the C ABI with host coordinates (atom sort + upload + splat + cc + readback)"}
     reps = 5
-    for _ in range(reps):
-        cc = vt.sim_cc(pos, radii, 5.0, S, gspacing=1.0)
-    vt.sync()
-    dt = (time.perf_counter() - t0) / reps
-    res["sim_cc_cfg1"] = {"voxels": S.gridsize(), "s_per_call": dt, "voxels_per_s": S.gridsize() / dt, "cc": cc,
-                          "note": "vt_sim_cc through the C ABI with host coordinates (atom sort + upload + splat + cc + readback)"}
-    # the same call with the library's own events around its kernels: what the device spends
-    vt.profile_reset(); vt.profile_enable(True)
-    for _ in range(reps):
-        vt.sim_cc(pos, radii, 5.0, S, gspacing=1.0)
-    vt.sync()
-    kms = sum(vt.profile_get(k)[0] for k in ("transform", "setup", "splat", "cc")) / reps
-    vt.profile_enable(False)
-    res["sim_cc_cfg1"]["kernel_ms_per_call"] = kms
-    res["sim_cc_cfg1"]["kernel_voxels_per_s"] = S.gridsize() / (kms * 1e-3) if kms > 0 else None
+    for name, thr in (("thr_minus_fltmax", -FLT_MAX), ("thr_0.1", 0.1)):
+        vt.sim_cc(pos, radii, 5.0, T, threshold=thr, gspacing=1.0)
+        vt.sync()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cc = vt.sim_cc(pos, radii, 5.0, T, threshold=thr, gspacing=1.0)
+        vt.sync()
+        dt = (time.perf_counter() - t0) / reps
+        # the same call with the library's own events around its kernels: what the device spends
+        vt.profile_reset(); vt.profile_enable(True)
+        for _ in range(reps):
+            vt.sim_cc(pos, radii, 5.0, T, threshold=thr, gspacing=1.0)
+        vt.sync()
+        kms = sum(vt.profile_get(k)[0] for k in ("transform", "setup", "splat", "cc")) / reps
+        vt.profile_enable(False)
+        out[name] = {"s_per_call": dt, "voxels_per_s": nvox / dt, "cc": cc, "kernel_ms_per_call": kms,
+                     "kernel_voxels_per_s": nvox / (kms * 1e-3) if kms > 0 else None}
     if not args.no_cpu:
         # the reference's CPU path on the same input: restated splat (OpenMP) + the reference's cc_threaded
         try:
-            from oracle.pyoracle import Grid as OGrid
             lib, kind = load_reference()
             threads = cpu_threads()
             if kind == "reference":
                 lib.set_numprocs(threads)
-            t0 = time.perf_counter()
-            og, od = lib.sim(pos, radii, quality, radscale, 1.0, nthreads=threads)
-            ccr = lib.ref_cc(og, od, og, od, -3.4028234663852886e38) if kind == "reference" else lib.cc(og, od, og, od, nthreads=threads)
-            dtc = time.perf_counter() - t0
-            res["sim_cc_cfg1"]["cpu"] = {"s_per_call": dtc, "voxels_per_s": og.n / dtc, "cores": threads, "kind": kind, "cc": ccr}
+            from oracle.pyoracle import Grid as OGrid
+            og = OGrid.make(tuple(S.grid.origin), (S.grid.xsize, S.grid.ysize, S.grid.zsize), 1.0)
+            tdata = T.data
+            cpu = {"cores": threads, "kind": kind}
+            for name, thr in (("thr_minus_fltmax", -FLT_MAX), ("thr_0.1", 0.1)):
+                t0 = time.perf_counter()
+                sg, sd = lib.sim(pos, radii, quality, radscale, 1.0, nthreads=threads)
+                ccr = lib.ref_cc(sg, sd, og, tdata, thr) if kind == "reference" else lib.cc(sg, sd, og, tdata, thr, nthreads=threads)
+                dtc = time.perf_counter() - t0
+                cpu[name] = {"s_per_call": dtc, "voxels_per_s": sg.n / dtc, "cc": ccr,
+                             "rel_err_gpu_vs_cpu": abs(out[name]["cc"] - ccr) / max(abs(ccr), 1e-30)}
+            out["cpu"] = cpu
         except Exception as e:  # the checker is optional for this leg
-            res["sim_cc_cfg1"]["cpu"] = {"unavailable": str(e)[:200]}
-    return res
+            out["cpu"] = {"unavailable": str(e)[:200]}
+    return out
 
 
 def cfg4_legs(vt, peaks, n):
@@ -505,7 +582,7 @@ def cfg4_legs(vt, peaks, n):
         vt.profile_reset(); vt.profile_enable(True)
         for _ in range(reps):
             fn()
-        ms, cnt = vt.profile_get(key)
+        ms = sum(vt.profile_get(k)[0] for k in key.split("+"))
         vt.profile_enable(False)
         return ms / reps
 
@@ -522,7 +599,8 @@ def cfg4_legs(vt, peaks, n):
     leg("diff", "binary", lambda: vt.subtract(A, B), 12)
     leg("add_offset", "binary", lambda: vt.add(A, B_off), 12)
     del B_off
-    leg("sigma", "stats", lambda: (A.scalar_add(0.0), A.sigma()), 8, note="mean pass + sigma pass, 4 B/voxel each")
+    leg("sigma", "stats+unary", lambda: A.sigma_scale(), 16,
+        note="`voltool sigma` = sigma_scale (TclVoltool.C:2167): mean pass + sigma pass + scale pass; in place, repeated")
     leg("binmask", "unary", lambda: B.binmask(0.5), 8, note="in place (repeated on the masked map)")
     del A, B
     return res
@@ -603,16 +681,9 @@ def cpu_eval_poses(lib, kind, pos, radii, com, g, t, tvol, poses, threads):
 
 
 def pose_host(lib, pos, com, q):
-    """rigid pose in plain numpy float32 (rotate about com by X, Y, Z Euler degrees, then shift)"""
-    p = (pos - com[None, :]).astype(np.float32)
-    for ax, deg in enumerate(q[:3]):
-        a = np.float32(np.deg2rad(float(deg)))
-        c, s = np.float32(np.cos(float(a))), np.float32(np.sin(float(a)))
-        i, j = [(1, 2), (2, 0), (0, 1)][ax]
-        pi, pj = p[:, i].copy(), p[:, j].copy()
-        p[:, i] = pi * c - pj * s
-        p[:, j] = pi * s + pj * c
-    return (p + com[None, :] + np.asarray(q[3:6], np.float32)[None, :]).astype(np.float32)
+    """one candidate of the pose list on the CPU: the oracle's restatement of rotate()'s transform
+    (TclVoltool.C:157-176) for float degrees, then the shift"""
+    return lib.pose_general(pos, com, q[:3], q[3:6]).reshape(-1, 3)
 
 
 def cpu_baseline(pos, radii, com, tmap, poses, budget_s=20.0):
@@ -640,7 +711,7 @@ def cpu_baseline(pos, radii, com, tmap, poses, budget_s=20.0):
     return {"value": done / dt, "unit": "poses/s", "cores": threads, "kind": kind,
             "sample": f"{done} poses of the same list, {dt:.1f} s; splat = documented restatement (QuickSurf not in the "
                       f"snapshot, OpenMP z-slabs), cc = {'the reference cc_threaded object code' if kind == 'reference' else 'C port of cc_threaded'}",
-            "cc_first": float(ccs[0])}
+            "cc_first": float(ccs[0]), "_ccs": [float(c) for c in ccs]}
 
 
 def run_reference(args):

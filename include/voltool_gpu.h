@@ -204,6 +204,20 @@ int vt_measure_center(const float *pos, const float *weight, long natoms, float 
    voltool_b200.dist).  merge(table, n, rank, world, user) must leave the complete table on every rank. */
 typedef int (*vt_table_merge_fn)(float *table, int n, int rank, int world, void *user);
 int vt_fit_set_shard(int rank, int world, vt_table_merge_fn merge, void *user);
+/* the same merge inside the library: ONE ncclAllGather per rotate() table on device buffers over NVLink (no
+   host round trip before the collective).  NCCL is bound at run time (dlopen libnccl.so.2; VOLTOOL_NCCL_LIB
+   overrides).  Rank 0 makes the 128-byte unique id, the caller carries it to the other ranks (MPI, a file,
+   torch.distributed), every rank calls vt_nccl_init, and vt_fit / vt_fit_sel then shard by themselves: rank r
+   evaluates candidates r, r + world, ... (TclVoltool.C:160-176) and all ranks replay the skip rule on the
+   identical merged table, so every rank returns the same pose. */
+int vt_nccl_unique_id(void *id_out, int len);
+int vt_nccl_init(int rank, int world, const void *id, int len);
+int vt_nccl_shutdown(void);
+/* per-shard best of an exhaustive pose list, on the device: out2 = {cc, (float)(index_base + arg max)}; NaN
+   entries never win, ties go to the lowest index (the order of `if (cc > best)`, TclVoltool.C:181) */
+int vt_fit_best_pose_device(const float *d_cc, long n, long index_base, float *d_best2);
+/* ncclAllGather of `count` floats per rank on the library stream (a device copy when no communicator is up) */
+int vt_nccl_allgather(const float *d_send, float *d_recv, long count);
 /* evaluator hook: by default the CUDA pose evaluator; host-logic tests inject their own */
 typedef int (*vt_table_eval_fn)(void *user, const float *origin_pos, const float com[3], int stride, int max_rot,
                                 int first, int step, float *table);
@@ -214,6 +228,24 @@ int vt_fit(float *pos, const float *radii, const float *mass, long natoms, const
    evaluator; dencom is vol_com(target) supplied by the caller.  No CUDA is touched. */
 int vt_fit_schedule(float *pos, const float *mass, long natoms, const float dencom[3], vt_table_eval_fn eval,
                     void *user, vt_fit_result *res);
+
+/* ---------------------------------------------------------------- atom selections
+ * The reference's AtomSel loops (`for i in firstsel..lastsel: if sel->on[i]`, moveby TclVoltool.C:52-59; the
+ * QuickSurf call sites TclMDFF.C:154-157, 496-499; fit's write-back :911-913) over the molecule's FULL arrays:
+ * pos = 3*num_atoms, radii/mass = num_atoms, on = num_atoms flags.  These compact by the flags (ascending atom
+ * index), run the compacted entry point above and scatter coordinates back; unselected atoms are untouched. */
+int vt_compact_selection(const float *pos, const float *radii, const float *mass, const int *on, long num_atoms,
+                         float *pos_out, float *radii_out, float *mass_out, long *index_out, long *nsel);
+int vt_sim_sel(const float *pos, const float *radii, const int *on, long num_atoms, int quality, float radscale,
+               float gspacing, vt_map **out);
+int vt_sim_cc_sel(const float *pos, const float *radii, const int *on, long num_atoms, double resolution,
+                  double gspacing_in, const vt_map *target, double threshold, double *cc, vt_map **synth_out);
+int vt_fit_sel(float *pos, const float *radii, const float *mass, const int *on, long num_atoms, const vt_map *target,
+               float resolution, vt_fit_result *res);
+/* what vt_fit_create chose: poses per batch (from the free device memory), workspaces (2 = two-stream
+   pipeline), whether the list-based splat is active, and whether the last device-list call had to redo its
+   cos/sin preparation on the host (see vt_fit_eval_poses_device).  Any pointer may be NULL. */
+int vt_fit_info(const vt_fit_ctx *ctx, int *batch, int *nslots, int *use_lists, int *prep_on_host);
 
 #ifdef __cplusplus
 }

@@ -131,6 +131,7 @@ class Oracle:
         L.vo_sim_policy.argtypes = [C.c_double, C.c_double, c_float_p, c_double_p, C.POINTER(C.c_int)]
         L.vo_measure_center.argtypes = [c_float_p, c_float_p, C.c_long, c_float_p]
         L.vo_pose_transform.argtypes = [c_float_p, C.c_long, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.vo_pose_general.argtypes = [c_float_p, C.c_long, c_float_p, c_float_p, c_float_p]
         L.vo_calc_cc.argtypes = [c_float_p, c_float_p, C.c_long, C.POINTER(Grid), c_float_p, C.c_float, C.c_int]
         L.vo_calc_cc.restype = C.c_double
         L.vo_rotate_table.argtypes = [c_float_p, c_float_p, C.c_long, c_float_p, C.c_int, C.c_int, C.POINTER(Grid),
@@ -280,6 +281,13 @@ class Oracle:
         p = f32(pos).copy()
         com = f32(com)
         self.lib.vo_pose_transform(fp(p), p.size // 3, fp(com), stride, x, y, z)
+        return p
+
+    def pose_general(self, pos, com, rot_deg, shift=(0.0, 0.0, 0.0)):
+        """one candidate of an explicit pose list: float degrees per axis, then a translation"""
+        p = f32(pos).copy()
+        com, rot, sh = f32(com), f32(rot_deg), f32(shift)
+        self.lib.vo_pose_general(fp(p), p.size // 3, fp(com), fp(rot), fp(sh))
         return p
 
     def calc_cc(self, pos, radii, gT, t, resolution, nthreads=1):

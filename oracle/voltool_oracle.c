@@ -1008,6 +1008,23 @@ void vo_pose_transform(float *pos, long natoms, const float com[3], int stride, 
   vo_moveby(pos, natoms, com);
 }
 
+/* one candidate of an explicit pose list (the translation-search extension of the fit path): the body of
+   rotate() (TclVoltool.C:157-176) with the integer `stride * amt` of do_rotate (:131-136) replaced by a
+   float number of degrees per axis, then moveby(shift).  shift = {0,0,0} and rot = stride * {x,y,z}
+   reproduces vo_pose_transform bit for bit (tests/test_oracle_vs_ref.py). */
+void vo_pose_general(float *pos, long natoms, const float com[3], const float rot_deg[3], const float shift[3]) {
+  float move1[3] = {-1.0f * com[0], -1.0f * com[1], -1.0f * com[2]};
+  float m[16];
+  vo_moveby(pos, natoms, move1);
+  for (int ax = 0; ax < 3; ax++) {
+    double amount = ((double)rot_deg[ax] * VO_PI / 180.0); /* DEGTORAD, utilities.h:49 */
+    vo_mat4_rot(m, ax, (float)amount);
+    vo_apply_mat(pos, natoms, m);
+  }
+  vo_moveby(pos, natoms, com);
+  vo_moveby(pos, natoms, shift);
+}
+
 static vo_cc_fn g_cc_fn = 0;
 static void *g_cc_ctx = 0;
 void vo_set_cc_backend(vo_cc_fn fn, void *ctx) { g_cc_fn = fn; g_cc_ctx = ctx; }

@@ -116,6 +116,7 @@ void vo_apply_mat(float *pos, long natoms, const float m[16]);
 void vo_measure_center(const float *pos, const float *w, long natoms, float com[3]);
 /* one candidate of rotate(): TclVoltool.C:165-176 */
 void vo_pose_transform(float *pos, long natoms, const float com[3], int stride, int x, int y, int z);
+void vo_pose_general(float *pos, long natoms, const float com[3], const float rot_deg[3], const float shift[3]);
 double vo_calc_cc(const float *pos, const float *radii, long natoms, const vo_grid *T, const float *t,
                   float resolution, int nthreads);
 

@@ -332,3 +332,51 @@ def test_mrc_modes_axis_order_and_byte_order(tmp_path):
         f.write(_mrc_header(4, 3, 2, 4) + b"\0" * 400)
     with pytest.raises(vt.VoltoolGpuError):
         vt.read_mrc(bad)
+
+
+def test_compact_selection_walks_like_atomsel():
+    """firstsel..lastsel, on[i] != 0, ascending (moveby TclVoltool.C:52-59); no GPU needed"""
+    r = np.random.default_rng(5)
+    n = 300
+    pos = r.random((n, 3)).astype(np.float32)
+    radii, mass = r.random(n).astype(np.float32), r.random(n).astype(np.float32)
+    on = (r.random(n) < 0.3).astype(np.int32)
+    on[:7] = 0
+    on[-5:] = 0
+    on[100] = 7                      # any nonzero flag selects
+    p, rd, m, idx = vt.compact_selection(pos, radii, mass, on)
+    want = np.flatnonzero(on)
+    assert np.array_equal(idx, want)
+    assert np.array_equal(bits(p), bits(pos[want])) and np.array_equal(bits(rd), bits(radii[want]))
+    assert np.array_equal(bits(m), bits(mass[want]))
+    p0, _, _, i0 = vt.compact_selection(pos, radii, mass, np.zeros(n, np.int32))
+    assert len(p0) == 0 and len(i0) == 0
+
+
+def test_pose_general_restates_pose_transform(oracle):
+    """the float-degree pose of the explicit pose lists == rotate()'s integer stride * amt candidate, and the
+    product's host transform has the same bits incl. the shift"""
+    r = np.random.default_rng(6)
+    pos = (r.random((200, 3)) * 60).astype(np.float32)
+    com = np.array([31.5, 28.25, 33.0], np.float32)
+    for stride, (x, y, z) in [(24, (2, 1, 13)), (4, (5, 0, 3)), (-4, (1, 2, 3)), (1, (3, 3, 0)), (-1, (0, 1, 2))]:
+        a = oracle.pose_transform(pos, com, stride, x, y, z)
+        b = oracle.pose_general(pos, com, (stride * x, stride * y, stride * z))
+        assert np.array_equal(bits(a), bits(b))
+    for rot, sh in [((12.5, -33.25, 359.999), (1.0, -1.0, 0.5)), ((90, 180, 270), (0, 0, 0)), ((0.001, 720.5, -400), (-2.5, 3, 1e-3))]:
+        want = oracle.pose_general(pos, com, rot, sh).reshape(-1, 3)
+        assert np.array_equal(bits(vt.pose_apply(pos, com, rot, sh)), bits(want))
+
+
+def test_nccl_binds_at_run_time():
+    """the library carries its own collective (vt_dist.cu): libnccl is found by dlopen and yields a unique id;
+    nothing is brought up without vt_init (no GPU here)"""
+    try:
+        uid = vt.nccl_unique_id()
+    except vt.VoltoolGpuError as e:
+        pytest.skip(f"no libnccl in this container: {e}")
+    assert len(uid) == 128 and any(uid)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(vt.VoltoolGpuError):
+            vt.nccl_init(0, 1, uid)

@@ -172,6 +172,18 @@ def lib():
     L.vt_fit_set_shard.argtypes = [C.c_int, C.c_int, MERGE_FN, C.c_void_p]
     L.vt_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, M, C.c_float, C.POINTER(FitResult)]
     L.vt_fit_schedule.argtypes = [C.c_void_p, C.c_void_p, C.c_long, c_float_p, EVAL_FN, C.c_void_p, C.POINTER(FitResult)]
+    IP, LP = C.POINTER(C.c_int), C.POINTER(C.c_long)
+    L.vt_compact_selection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, LP]
+    L.vt_sim_sel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_float, C.POINTER(M)]
+    L.vt_sim_cc_sel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_double, C.c_double, M, C.c_double,
+                                C.POINTER(C.c_double), C.POINTER(M)]
+    L.vt_fit_sel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, M, C.c_float, C.POINTER(FitResult)]
+    L.vt_fit_info.argtypes = [C.c_void_p, IP, IP, IP, IP]
+    L.vt_nccl_unique_id.argtypes = [C.c_void_p, C.c_int]
+    L.vt_nccl_init.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.vt_fit_best_pose_device.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_void_p]
+    L.vt_nccl_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
     _lib = L
     return L
 
@@ -476,6 +488,29 @@ def cc_threaded(qs_vol, target_vol, threshold=-FLT_MAX, full=False):
     return (cc.value, n.value, list(sums)) if full else cc.value
 
 
+def cc_host(grid_a, a, grid_b, b, threshold=-FLT_MAX):
+    """vt_cc_host: the body INTEGRATION.md gives cc_threaded (host arrays in, cc out)"""
+    _need()
+    a, b = f32(a).reshape(-1), f32(b).reshape(-1)
+    cc = C.c_double()
+    _check(lib().vt_cc_host(C.byref(grid_a), _vp(a), C.byref(grid_b), _vp(b), threshold, C.byref(cc)), "vt_cc_host")
+    return cc.value
+
+
+def binary_host(op, grid_a, a, grid_b, b, interp=True, use_union=False):
+    """vt_binary_host: host arrays in, (Grid, float32 array) out"""
+    _need()
+    a, b = f32(a).reshape(-1), f32(b).reshape(-1)
+    g, p = Grid(), c_float_p()
+    _check(lib().vt_binary_host(op, int(interp), int(use_union), C.byref(grid_a), _vp(a), C.byref(grid_b), _vp(b),
+                                C.byref(g), C.byref(p)), "vt_binary_host")
+    try:
+        out = np.ctypeslib.as_array(p, shape=(max(g.n, 1),))[:g.n].copy()
+    finally:
+        lib().vt_free_host(p)
+    return g, out
+
+
 def binary(op, map_a, map_b, interp=True, use_union=False):
     h = C.c_void_p()
     _check(lib().vt_binary(op, int(interp), int(use_union), map_a.h, map_b.h, C.byref(h)), "vt_binary")
@@ -544,6 +579,75 @@ def sim_cc(pos, radii, resolution, target, threshold=-FLT_MAX, gspacing=0.0, wan
     return (cc.value, VolMap(_handle=h)) if want_synth else cc.value
 
 
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
+
+
+def compact_selection(pos, radii, mass, on):
+    """the AtomSel walk of the reference (firstsel..lastsel, on[i]): returns compacted pos, radii, mass, indices"""
+    pos, radii, mass, on = f32(pos).reshape(-1), f32(radii).reshape(-1), f32(mass).reshape(-1), _i32(on)
+    n = on.size
+    po, ro, mo = np.empty(3 * n, np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
+    io, k = np.empty(n, np.int64), C.c_long()
+    _check(lib().vt_compact_selection(_vp(pos), _vp(radii), _vp(mass), _vp(on), n, _vp(po), _vp(ro), _vp(mo), _vp(io),
+                                      C.byref(k)), "vt_compact_selection")
+    k = k.value
+    return po[:3 * k].reshape(-1, 3).copy(), ro[:k].copy(), mo[:k].copy(), io[:k].copy()
+
+
+def sim_sel(pos, radii, on, quality, radscale, gspacing):
+    _need()
+    pos, radii, on = f32(pos).reshape(-1), f32(radii).reshape(-1), _i32(on)
+    h = C.c_void_p()
+    _check(lib().vt_sim_sel(_vp(pos), _vp(radii), _vp(on), on.size, quality, radscale, gspacing, C.byref(h)), "vt_sim_sel")
+    return VolMap(_handle=h)
+
+
+def sim_cc_sel(pos, radii, on, resolution, target, threshold=-FLT_MAX, gspacing=0.0):
+    _need()
+    pos, radii, on = f32(pos).reshape(-1), f32(radii).reshape(-1), _i32(on)
+    cc = C.c_double()
+    _check(lib().vt_sim_cc_sel(_vp(pos), _vp(radii), _vp(on), on.size, resolution, gspacing, target.h, threshold,
+                               C.byref(cc), None), "vt_sim_cc_sel")
+    return cc.value
+
+
+def fit_sel(pos, radii, mass, on, target, resolution):
+    """fit() on the selected atoms of the molecule's full arrays; unselected coordinates come back untouched"""
+    _need()
+    p, radii, mass, on = f32(pos).reshape(-1).copy(), f32(radii).reshape(-1), f32(mass).reshape(-1), _i32(on)
+    res = FitResult()
+    _check(lib().vt_fit_sel(_vp(p), _vp(radii), _vp(mass), _vp(on), on.size, target.h, resolution, C.byref(res)), "vt_fit_sel")
+    return p.reshape(-1, 3), res
+
+
+def nccl_unique_id():
+    """128-byte NCCL unique id (rank 0 makes it; the caller carries it to the other ranks)"""
+    buf = C.create_string_buffer(128)
+    _check(lib().vt_nccl_unique_id(buf, 128), "vt_nccl_unique_id")
+    return buf.raw
+
+
+def nccl_init(rank, world, uid):
+    """bring up the library's own communicator: vt_fit then shards its pose search and merges over NCCL"""
+    _need()
+    buf = C.create_string_buffer(bytes(uid), 128)
+    _check(lib().vt_nccl_init(rank, world, buf, 128), "vt_nccl_init")
+
+
+def nccl_shutdown():
+    if _lib is not None:
+        _lib.vt_nccl_shutdown()
+
+
+def best_pose_device(d_cc_ptr, n, index_base, d_best2_ptr):
+    _check(lib().vt_fit_best_pose_device(C.c_void_p(d_cc_ptr), n, index_base, C.c_void_p(d_best2_ptr)), "vt_fit_best_pose_device")
+
+
+def nccl_allgather(d_send_ptr, d_recv_ptr, count):
+    _check(lib().vt_nccl_allgather(C.c_void_p(d_send_ptr), C.c_void_p(d_recv_ptr), count), "vt_nccl_allgather")
+
+
 def rotate_replay(table, max_rot, returncc):
     table = f32(table)
     cc, bi = C.c_float(returncc), C.c_int(-1)
@@ -588,6 +692,12 @@ class FitContext:
             self.close()
         except Exception:
             pass
+
+    def info(self):
+        """what vt_fit_create chose (poses per batch, workspaces, list splat) + the host-preparation flag"""
+        v = [C.c_int() for _ in range(4)]
+        _check(lib().vt_fit_info(self.h, *[C.byref(x) for x in v]), "vt_fit_info")
+        return {"batch": v[0].value, "nslots": v[1].value, "use_lists": bool(v[2].value), "prep_on_host": bool(v[3].value)}
 
     def set_origin(self, pos):
         pos = f32(pos).reshape(-1)

@@ -5,6 +5,8 @@
 #include <cstring>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "vt_device.cuh"
 
 namespace vt {
@@ -23,7 +25,11 @@ void set_error(const char *fmt, ...) {
   if (getenv("VOLTOOL_VERBOSE")) fprintf(stderr, "[voltool_gpu] %s\n", g_err);
 }
 
+static cudaError_t g_last_cuda = cudaSuccess;
+cudaError_t last_cuda_error() { return g_last_cuda; }
+
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  g_last_cuda = e;
   set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
   return 2;
 }
@@ -42,13 +48,18 @@ static cudaEvent_t take_event() {
   cudaEventCreate(&e);
   return e;
 }
+NvtxScope::NvtxScope(const char *name) { nvtxRangePushA(name); }
+NvtxScope::~NvtxScope() { nvtxRangePop(); }
+
 void prof_begin(int key) {
+  nvtxRangePushA(kProfNames[key]);   // kernel-class range (splat, pose_cc, blur, ...) inside the entry point's range
   if (!g_prof_on) return;
   ProfSpan s{take_event(), take_event(), key, false};
   cudaEventRecord(s.a, g_ctx.stream);
   g_spans.push_back(s);
 }
 void prof_end(int key) {
+  nvtxRangePop();
   if (!g_prof_on) return;
   for (size_t i = g_spans.size(); i-- > 0;)
     if (g_spans[i].key == key && !g_spans[i].closed) {

@@ -29,6 +29,7 @@ Ctx &ctx();
 bool ctx_ready();
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+cudaError_t last_cuda_error();   // the error of the most recent cuda_fail (to tell an allocation failure from a fault)
 
 #define VT_CUDA(expr)                                                       \
   do {                                                                      \
@@ -41,13 +42,22 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     cudaError_t _e = cudaGetLastError();                                    \
     if (_e != cudaSuccess) return ::vt::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
   } while (0)
+// every entry point opens with this: the context check, then an NVTX range named after the function for as long as
+// the call runs (the reference brackets its commands with PROFILE_PUSH_RANGE / PROFILE_POP_RANGE, TclMDFF.C:383,
+// 551, 603; nested library calls nest their ranges).  nvtx3 is header-only and costs nothing without a tool attached.
 #define VT_REQUIRE_CTX()                                                    \
   do {                                                                      \
     if (!::vt::ctx_ready()) {                                               \
       ::vt::set_error("voltool_gpu: vt_init() has not succeeded (no CUDA device, no CPU fallback)"); \
       return 1;                                                             \
     }                                                                       \
-  } while (0)
+  } while (0);                                                              \
+  ::vt::NvtxScope vt_nvtx_scope_(__func__)
+
+struct NvtxScope {
+  explicit NvtxScope(const char *name);
+  ~NvtxScope();
+};
 
 // optional per-kernel CUDA-event timing on the library stream (bench.py's roofline leg)
 enum ProfKey { PK_TRANSFORM = 0, PK_SETUP, PK_SPLAT, PK_POSE_CC, PK_POSE_FINISH, PK_CC, PK_STATS, PK_UNARY, PK_BINARY,

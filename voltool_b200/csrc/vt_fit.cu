@@ -1,5 +1,6 @@
 // vt_fit.cu -- C ABI of sim / calc_cc / fit over the batched pose pipeline (vt_sim.cu).
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -7,6 +8,10 @@
 #include "vt_pose.cuh"
 
 using namespace vt;
+
+namespace vt {
+int nccl_merge_table(const float *d_slice, float *table, int n);   // vt_dist.cu
+}
 
 // Two pose-batch workspaces: while batch i splats and scores on the library stream, batch i+1 is
 // transformed, binned and listed on a second stream (those kernels are small and latency-bound, so
@@ -26,6 +31,8 @@ struct vt_fit_ctx {
   PrepPose *d_prep = nullptr;  // prepared poses of the whole call
   long d_prep_cap = 0;
   float *d_cc = nullptr;       // results of the current call
+  int *d_flag = nullptr;       // ambiguous-cast counter of prep_from_pose_kernel
+  int last_prep_on_host = 0;   // the last device-list call fell back to the host preparation
   long cc_cap = 0;
 };
 
@@ -127,20 +134,39 @@ int sim_to_map(const float *pos, const float *radii, long natoms, int quality, f
   return rc;
 }
 
-__global__ void prep_from_pose_kernel(const vt_pose *__restrict__ poses, int n, PrepPose *__restrict__ out) {
+// (float) of a double whose last few ulps are uncertain: true when a float rounding boundary lies within ~9
+// double ulps of d, i.e. when the cast of a differently rounded evaluation of the same function could differ
+__device__ __forceinline__ bool float_cast_ambiguous(double d) {
+  const float f = (float)d;
+  const double fd = (double)f;
+  const double up = (double)nextafterf(f, INFINITY), dn = (double)nextafterf(f, -INFINITY);
+  const double tol = fabs(d) * 2.0e-15 + 1e-300;
+  return fabs(d - 0.5 * (fd + up)) <= tol || fabs(d - 0.5 * (fd + dn)) <= tol;
+}
+
+// device twin of euler_cs (vt_host.cpp; do_rotate TclVoltool.C:131-136).  CUDA's double cos/sin are good to
+// 2 ulp, glibc's to <1 ulp: after the cast to float the two agree unless the double lies within a few ulps of a
+// float rounding boundary (about 3 in 10^8 evaluations).  Those poses raise *ambiguous and the caller redoes
+// the preparation on the host, so a device pose list always scores exactly like the host list.
+__global__ void prep_from_pose_kernel(const vt_pose *__restrict__ poses, int n, PrepPose *__restrict__ out,
+                                      int *__restrict__ ambiguous) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const vt_pose q = poses[i];
   PrepPose r;
+  bool amb = false;
   for (int k = 0; k < 3; ++k) {
     // DEGTORAD in double, rotate_axis takes a float angle, cos/sin evaluated in double
     const double amount = (double)q.rot_deg[k] * 3.14159265358979323846 / 180.0;
     const float a = (float)amount;
-    r.c[k] = (float)cos((double)a);
-    r.s[k] = (float)sin((double)a);
+    const double cd = cos((double)a), sd = sin((double)a);
+    amb = amb || float_cast_ambiguous(cd) || float_cast_ambiguous(sd);
+    r.c[k] = (float)cd;
+    r.s[k] = (float)sd;
     r.shift[k] = q.shift[k];
   }
   out[i] = r;
+  if (amb) atomicAdd(ambiguous, 1);
 }
 
 int ensure_cc_buffer(vt_fit_ctx *f, long n) {
@@ -254,7 +280,12 @@ int cuda_table_eval(void *user, const float *origin_pos, const float com[3], int
   vt_fit_ctx *f = (vt_fit_ctx *)user;
   int rc = vt_fit_set_origin(f, origin_pos);
   if (rc) return rc;
-  return vt_fit_rotate_table(f, com, stride, max_rot, first, step, table);
+  rc = vt_fit_rotate_table(f, com, stride, max_rot, first, step, table);
+  if (rc) return rc;
+  // sharded over NCCL: this rank's slice is still in f->d_cc in evaluation order (candidates first, first + step,
+  // ...): one allgather of the device slices, and every rank holds the whole table
+  if (step > 1 && nccl_active() && !shard_config().merge) rc = nccl_merge_table(f->d_cc, table, max_rot * max_rot * max_rot);
+  return rc;
 }
 
 }  // namespace
@@ -334,27 +365,62 @@ int vt_fit_create(const float *pos, const float *radii, long natoms, const vt_ma
   const int quality = resolution >= 9 ? 0 : 3;
   int rc = atomset_create(pos, radii, natoms, make_params(quality, radscale, (float)gspacing), f->as);
   if (rc) { delete f; return rc; }
-  const char *env = getenv("VOLTOOL_FIT_BATCH");
-  {
-    // poses per batch: 256 while a pose's density grid stays small (cfg2: 2.6 MB), 128 for big structures, where
-    // the per-pose workspace (grid, lists, boxes) is what limits it (measured on cfg2: 128 -> 256 poses: +2.8 %)
-    const double ext = 2.0 * f->as.bound_radius + 2.0 * f->as.pad + 4.0 * gspacing;
-    const double cap_n = std::ceil(ext / gspacing) + 2.0;
-    f->B = env ? atoi(env) : (cap_n * cap_n * cap_n * 4.0 <= 8.0e6 ? 256 : 128);
-  }
-  if (f->B < 1) f->B = 1;
-  if (f->B > 1024) f->B = 1024;
   const char *ov = getenv("VOLTOOL_FIT_OVERLAP");
   f->nslots = (ov && atoi(ov) == 0) ? 1 : 2;
-  for (int k = 0; k < f->nslots && !rc; ++k) {
-    rc = batch_create(f->as, &target->grid, f->B, f->pb[k]);
-    if (!rc) {
-      const float com0[3] = {0.f, 0.f, 0.f};
-      rc = batch_prepare(f->as, f->pb[k], 1, nullptr, com0, 1, &target->grid);
-      if (!rc) rc = batch_calibrate_lists(f->as, f->pb[k]);
-      if (f->nslots > 1) f->pb[k].splat_ctas = 5;   // leave room for the second stream (vt_splat2.cu)
+  // poses per batch: 256 while a pose's density grid stays small (cfg2: 2.6 MB), 128 for big structures
+  // (measured on cfg2: 128 -> 256 poses: +2.8 %), and never more than fits: the reference evaluates poses one
+  // at a time, so any structure it can fit must fit here too.  The per-pose workspace is estimated from the
+  // capacities batch_create will use, B is cut to 80 % of the free device memory, and an allocation that
+  // still fails halves B (and finally drops the second workspace).  VOLTOOL_FIT_BATCH only overrides the start.
+  {
+    const double ext = 2.0 * f->as.bound_radius + 2.0 * f->as.pad + 4.0 * gspacing;
+    const double cap_n = std::ceil(ext / gspacing) + 2.0;
+    const double grid_bytes = cap_n * cap_n * cap_n * 4.0;
+    const char *env = getenv("VOLTOOL_FIT_BATCH");
+    f->B = env ? atoi(env) : (grid_bytes <= 8.0e6 ? 256 : 128);
+    if (f->B < 1) f->B = 1;
+    if (f->B > 1024) f->B = 1024;
+    const double tiles = std::ceil(cap_n / kTX) * std::ceil(cap_n / kTY) * std::ceil(cap_n / kTZ);
+    const double nwords = (f->as.ngroups + 31) / 32;
+    const double h = std::ceil((double)f->as.prm.gausslim * f->as.maxrad * radscale / gspacing) + 1.0;
+    const double reach = (kTX + 2 * h) * (kTY + 2 * h) * (kTZ + 2 * h);
+    const double list_cap = 1.6 * 2.0 * (double)f->as.n * reach / (cap_n * cap_n * cap_n) + 256.0;   // per tile, as calibrated
+    const double per_pose = grid_bytes + 28.0 * f->as.n + 28.0 * f->as.ngroups + tiles * (4.0 * nwords + 4.0 + 4.0 * list_cap) +
+                            6.0 * sizeof(geom::AxisEntry) * (cap_n * 1.6 + 8) + 48.0 * (cap_n * cap_n * cap_n / (32.0 * kRowsFit * kZChunkFit) + 64);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_pose > 0) {
+      // memory the pool already holds but has handed back to us is reusable as well
+      cudaMemPool_t pool = nullptr;
+      unsigned long long reserved = 0, used = 0;
+      if (cudaDeviceGetDefaultMemPool(&pool, ctx().device) == cudaSuccess &&
+          cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+          cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+        free_b += (size_t)(reserved - used);
+      const double fit_b = 0.8 * (double)free_b / (f->nslots * per_pose);
+      if (fit_b < f->B) f->B = fit_b < 1.0 ? 1 : (int)fit_b;
     }
   }
+  while (true) {
+    rc = 0;
+    for (int k = 0; k < f->nslots && !rc; ++k) {
+      rc = batch_create(f->as, &target->grid, f->B, f->pb[k]);
+      if (!rc) {
+        const float com0[3] = {0.f, 0.f, 0.f};
+        rc = batch_prepare(f->as, f->pb[k], 1, nullptr, com0, 1, &target->grid);
+        if (!rc) rc = batch_calibrate_lists(f->as, f->pb[k]);
+        if (f->nslots > 1) f->pb[k].splat_ctas = 5;   // leave room for the second stream (vt_splat2.cu)
+      }
+    }
+    if (rc != 2 || last_cuda_error() != cudaErrorMemoryAllocation) break;
+    for (int k = 0; k < 2; ++k) batch_destroy(f->pb[k]);
+    cudaGetLastError();
+    if (f->B > 1) f->B = (f->B + 1) / 2;
+    else if (f->nslots > 1) f->nslots = 1;
+    else break;
+  }
+  if (getenv("VOLTOOL_VERBOSE"))
+    fprintf(stderr, "voltool_gpu: fit workspace: %d poses per batch x %d slot(s), lists %s\n", f->B, f->nslots,
+            f->pb[0].use_lists ? "on" : "off");
   if (!rc && f->nslots > 1) {
     cudaError_t e = cudaStreamCreateWithFlags(&f->aux, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_start, cudaEventDisableTiming);
@@ -383,8 +449,18 @@ int vt_fit_destroy(vt_fit_ctx *f) {
   atomset_destroy(f->as);
   dev_free(f->d_cc);
   dev_free(f->d_prep);
+  dev_free(f->d_flag);
   if (f->h_prep) cudaFreeHost(f->h_prep);
   delete f;
+  return 0;
+}
+
+int vt_fit_info(const vt_fit_ctx *f, int *batch, int *nslots, int *use_lists, int *prep_on_host) {
+  if (!f) { set_error("vt_fit_info: null context"); return 1; }
+  if (batch) *batch = f->B;
+  if (nslots) *nslots = f->nslots;
+  if (use_lists) *use_lists = f->pb[0].use_lists ? 1 : 0;
+  if (prep_on_host) *prep_on_host = f->last_prep_on_host;
   return 0;
 }
 
@@ -428,22 +504,43 @@ int vt_fit_eval_poses_device(vt_fit_ctx *f, const float com[3], const vt_pose *d
   VT_REQUIRE_CTX();
   if (nposes <= 0) return 0;
   Ctx &c = ctx();
-  int rc = ensure_prep_buffers(f, nposes, false);
-  if (!rc) rc = reset_overflow(f);
-  if (rc) return rc;
-  prep_from_pose_kernel<<<(unsigned int)((nposes + 127) / 128), 128, 0, c.stream>>>(d_poses, (int)nposes, f->d_prep);
-  VT_LAUNCHED();
-  rc = eval_prepared(f, com, f->d_prep, nposes, d_cc);
-  if (rc) return rc;
-  // one 4-byte readback per workspace and call: a truncated tile list must never go unnoticed
-  int ovf = 0;
-  rc = any_overflow(f, &ovf);
-  if (rc) return rc;
-  if (ovf) {
-    for (int k = 0; k < 2; ++k) f->pb[k].use_lists = false;
-    return vt_fit_eval_poses_device(f, com, d_poses, nposes, d_cc);
+  bool host_prep = getenv("VOLTOOL_PREP_HOST") != nullptr;   // tests: force the host preparation
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    int rc = ensure_prep_buffers(f, nposes, host_prep);
+    if (!rc && !f->d_flag) rc = dev_alloc((void **)&f->d_flag, sizeof(int));
+    if (!rc) rc = reset_overflow(f);
+    if (rc) return rc;
+    VT_CUDA(cudaMemsetAsync(f->d_flag, 0, sizeof(int), c.stream));
+    if (!host_prep) {
+      prep_from_pose_kernel<<<(unsigned int)((nposes + 127) / 128), 128, 0, c.stream>>>(d_poses, (int)nposes, f->d_prep,
+                                                                                         f->d_flag);
+      VT_LAUNCHED();
+    } else {   // cos/sin with the host libm, exactly as vt_fit_eval_poses forms them
+      std::vector<vt_pose> hp((size_t)nposes);
+      VT_CUDA(cudaMemcpyAsync(hp.data(), d_poses, sizeof(vt_pose) * (size_t)nposes, cudaMemcpyDeviceToHost, c.stream));
+      VT_CUDA(cudaStreamSynchronize(c.stream));
+      for (long i = 0; i < nposes; ++i)
+        for (int k = 0; k < 3; ++k) {
+          euler_cs((double)hp[i].rot_deg[k], f->h_prep[i].c[k], f->h_prep[i].s[k]);
+          f->h_prep[i].shift[k] = hp[i].shift[k];
+        }
+      VT_CUDA(cudaMemcpyAsync(f->d_prep, f->h_prep, sizeof(PrepPose) * (size_t)nposes, cudaMemcpyHostToDevice, c.stream));
+    }
+    rc = eval_prepared(f, com, f->d_prep, nposes, d_cc);
+    if (rc) return rc;
+    // one small readback per call: a truncated tile list or an ambiguous cast must never go unnoticed
+    int amb = 0;
+    VT_CUDA(cudaMemcpyAsync(&amb, f->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    VT_CUDA(cudaStreamSynchronize(c.stream));
+    int ovf = 0;
+    rc = any_overflow(f, &ovf);
+    if (rc) return rc;
+    if (!ovf && !amb) { f->last_prep_on_host = host_prep ? 1 : 0; return 0; }
+    if (ovf) for (int k = 0; k < 2; ++k) f->pb[k].use_lists = false;
+    if (amb) host_prep = true;
   }
-  return 0;
+  set_error("vt_fit_eval_poses_device: no clean pass after 4 attempts");
+  return 3;
 }
 
 int vt_fit_rotate_table(vt_fit_ctx *f, const float com[3], int stride, int max_rot, int first, int step,

@@ -9,11 +9,6 @@
 
 namespace vt {
 
-struct ShardConfig {
-  int rank = 0, world = 1;
-  vt_table_merge_fn merge = nullptr;
-  void *user = nullptr;
-};
 static ShardConfig g_shard;
 const ShardConfig &shard_config() { return g_shard; }
 
@@ -27,7 +22,7 @@ extern "C" {
 
 int vt_fit_set_shard(int rank, int world, vt_table_merge_fn merge, void *user) {
   if (world < 1 || rank < 0 || rank >= world) return 1;
-  if (world > 1 && !merge) return 1;
+  if (world > 1 && !merge && !nccl_active()) return 1;   // without a callback the tables must merge over NCCL
   g_shard.rank = rank; g_shard.world = world; g_shard.merge = merge; g_shard.user = user;
   return 0;
 }
@@ -87,7 +82,7 @@ int vt_fit_schedule(float *pos, const float *mass, long natoms, const float denc
     std::vector<float> table(total, NAN);
     int rc = eval(user, origin.data(), com, stride, m, sh.rank, sh.world, table.data());
     if (rc) return rc;
-    if (sh.world > 1) {
+    if (sh.world > 1 && sh.merge) {   // (no callback: the evaluator returned the merged table, vt_dist.cu)
       rc = sh.merge(table.data(), total, sh.rank, sh.world, sh.user);
       if (rc) return rc;
     }

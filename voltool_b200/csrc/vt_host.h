@@ -71,4 +71,13 @@ void pose_apply(float *pos, long natoms, const float com[3], const vt_pose &pose
 void measure_center(const float *pos, const float *w, long natoms, float com[3]);
 int rotate_replay(const float *table, int max_rot, float *returncc, int *best_idx);
 
+// how the pose search is sharded (vt_fit_set_shard / vt_nccl_init): rank r evaluates candidates r, r + world, ...
+struct ShardConfig {
+  int rank = 0, world = 1;
+  vt_table_merge_fn merge = nullptr;   // host-side merge callback; nullptr with world > 1: the evaluator merges (NCCL)
+  void *user = nullptr;
+};
+const ShardConfig &shard_config();
+bool nccl_active();                    // vt_dist.cu: a communicator is up, tables merge on the device
+
 }  // namespace vt

@@ -36,6 +36,25 @@ def table_merge_allgather(table, rank, world, device=None):
 _keep = []
 
 
+def init_nccl_from_torch(device=None):
+    """bring up the LIBRARY's NCCL communicator (vt_nccl_init) for the ranks of the current torch.distributed job:
+    rank 0 makes the unique id, torch carries it (one 128-byte broadcast), every rank joins.  After this vt_fit
+    shards by itself and merges its per-stage tables with one ncclAllGather on device buffers."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    backend = dist.get_backend()
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else "cpu")
+    t = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(api.nccl_unique_id()), dtype=torch.uint8).clone()
+    t = t.to(dev)
+    dist.broadcast(t, 0)
+    api.nccl_init(rank, world, bytes(t.cpu().numpy().tobytes()))
+    return rank, world
+
+
+
 def install_shard(rank=None, world=None, device=None):
     """register this process as shard `rank` of `world` with the C library (vt_fit_set_shard)"""
     import torch.distributed as dist
