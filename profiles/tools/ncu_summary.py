@@ -3,6 +3,7 @@
 metrics, the hottest source lines (instructions, stall samples, shared-memory wavefronts) and the
 SASS opcode mix.  Usage: ncu_summary.py report.ncu-rep kernel_substring [title]"""
 import collections
+import os
 import csv
 import io
 import re
@@ -65,7 +66,8 @@ def main():
                             pass
     ti, ts, tw = sum(x[3] for x in lines) or 1, sum(x[4] for x in lines) or 1, sum(x[5] for x in lines) or 1
     print(f"\nsource lines: {ti:.3e} warp instructions, {ts} stall samples, {tw:.3e} shared-memory wavefronts")
-    for x in sorted(lines, key=lambda x: -x[3])[:14]:
+    key = 4 if os.environ.get('NCU_SORT') == 'smp' else 3
+    for x in sorted(lines, key=lambda x: -x[key])[:int(os.environ.get('NCU_TOP', 14))]:
         print(f" {100 * x[3] / ti:5.1f}% inst {100 * x[4] / ts:5.1f}% smp {100 * x[5] / tw:5.1f}% smem  {x[0]}:{x[1]}  {x[2]}")
     to = sum(ops.values()) or 1
     print("\nopcode mix: " + ", ".join(f"{k} {100 * v / to:.1f}%" for k, v in ops.most_common(14)))

@@ -380,13 +380,17 @@ def test_supersample_known_answers():
     assert np.all(const == 2.5)
 
 
-@pytest.mark.parametrize("mode", ["", "yz", "xyz"])
-@pytest.mark.parametrize("sigma", [0.6, 1.5, 2.0])
+@pytest.mark.parametrize("mode", ["", "yz", "xyz", "tma", "tma_plain"])
+@pytest.mark.parametrize("sigma", [0.3, 0.6, 1.0, 1.5, 2.0, 2.5])
 def test_blur_bit_exact(oracle, sigma, mode, monkeypatch):
-    """default path and the x | y+z form (z pass as a register scatter), incl. maps thinner than the radius"""
+    """every form of the blur (two-kernel default, x | y+z with the z pass as a register scatter, the cp.async
+    one-kernel form, the tensor-map TMA one-pass form and its plain-load twin), incl. maps thinner than the radius,
+    several tiles per axis and ragged tile edges"""
     if mode:
-        monkeypatch.setenv("VOLTOOL_BLUR_MODE", mode)
-    for size in [(20, 17, 15), (64, 9, 33), (5, 4, 3), (36, 35, 70), (8, 3, 2), (132, 40, 5)]:
+        monkeypatch.setenv("VOLTOOL_BLUR_MODE", mode[:3])
+        if mode == "tma_plain":      # same kernel, the planes staged by plain clamped loads instead of TMA
+            monkeypatch.setenv("VOLTOOL_BLUR_NOTMA", "1")
+    for size in [(20, 17, 15), (64, 9, 33), (5, 4, 3), (36, 35, 70), (8, 3, 2), (132, 40, 5), (48, 130, 40), (100, 70, 90)]:
         g = OGrid.make((0, 0, 0), size, 1.0)
         d = rng_map(9, g.n)
         m = vt.VolMap(G(g), d).gaussian_blur(sigma)

@@ -750,6 +750,8 @@ static int blur_fixed(const float *src, float *dst, float *tmp, int nx, int ny, 
   return 0;
 }
 
+int k_blur_tma(const float *src, float *dst, int nx, int ny, int nz, const float *w, int R);
+
 int k_blur(const float *src, float *dst, float *tmp, int nx, int ny, int nz, const float *w, int R) {
   VT_REQUIRE_CTX();
   Ctx &c = ctx();
@@ -760,7 +762,12 @@ int k_blur(const float *src, float *dst, float *tmp, int nx, int ny, int nz, con
   if (grid < 1) grid = 1;
   // x: src -> dst ; y: dst -> tmp ; z: tmp -> dst
   prof_begin(PK_BLUR);
-  const char *bmode = getenv("VOLTOOL_BLUR_MODE");   // "yz": x pass + fused y/z pass; default: fused x/y pass + z pass
+  const char *bmode = getenv("VOLTOOL_BLUR_MODE");
+  if (bmode && !strcmp(bmode, "tma")) {   // one pass over HBM, tensor-map TMA staging (vt_blur_tma.cu)
+    const int rc = k_blur_tma(src, dst, nx, ny, nz, w, R);
+    if (rc == 0) { prof_end(PK_BLUR); return 0; }
+    if (rc > 1) return rc;
+  }   // "yz": x pass + fused y/z pass; default: fused x/y pass + z pass
   if (bmode && !strcmp(bmode, "xyz")) {   // all three passes in one kernel
     int rc = 1;
     switch (R) {
