@@ -156,6 +156,17 @@ int vt_calc_cc(const float *pos, const float *radii, long natoms, const vt_map *
 int vt_sim_cc(const float *pos, const float *radii, long natoms, double resolution, double gspacing_in,
               const vt_map *target, double threshold, double *cc, vt_map **synth_out /* may be NULL */);
 
+/* `voltool cc -calcsynthmap -calcdiffmap -calcspatialccmap` (usage TclMDFF.C:180-184, plumbing :555-594).  The
+   reference fills the last two only inside vmd_cuda_compare_sel_refmap (CUDAMDFF.cu, not in the snapshot); the
+   definition built here (vt_ccmaps.cu, oracle twin vo_cc_maps): on G = init_from_intersection(A, B), the grid
+   cc_threaded walks, diff = sample(A) - sample(B); spatial = the CC expression of MDFF.C:143-149 per 8x8x8 tile
+   of G (grid: ceil(n/8) tiles per axis on G's origin, one cell = 8 cells of G; 0 for a tile without voxels);
+   *cc = the same expression on the tile sums.  diff_out / spatial_out may be NULL. */
+int vt_cc_maps(const vt_map *A, const vt_map *B, double threshold, double *cc, vt_map **diff_out, vt_map **spatial_out);
+int vt_sim_cc_maps(const float *pos, const float *radii, long natoms, double resolution, double gspacing_in,
+                   const vt_map *target, double threshold, double *cc, vt_map **synth_out, vt_map **diff_out,
+                   vt_map **spatial_out);
+
 /* ---------------------------------------------------------------- fit (rigid-body pose search) */
 /* one candidate of rotate() (TclVoltool.C:160-176) or of an explicit pose list: rotate about
    com by Euler angles (degrees, X then Y then Z, each a separate rounded pass like do_rotate
@@ -198,6 +209,25 @@ int vt_rotate_replay(const float *table, int max_rot, float *returncc, int *best
 /* apply one candidate transform to host coordinates with the reference's rounding (do_rotate etc.) */
 int vt_pose_apply(float *pos, long natoms, const float com[3], const vt_pose *pose);
 int vt_measure_center(const float *pos, const float *weight, long natoms, float com[3]); /* TclVoltool.C:789 */
+
+/* density_rotate (TclVoltool.C:202-279, dead code: caller commented out at :820-891): the map-rotating search.
+   Per candidate (x, y, z) < max_rot^3 the synthetic map's frame is moved by -com, rotated about X, Y, Z by
+   stride * amt degrees (do_density_rotate :138-149 -> vol_move), its vol_com put back onto com, and
+   cc_threaded(target, synth, 0.1) kept if `cc > *returncc`.  synth's frame is restored from true copies on return
+   (the dead caller aliases the copies with the live arrays, :874-877; see vt_density.cu).  table (may be NULL)
+   receives all max_rot^3 scores in loop order. */
+int vt_density_rotate(const vt_map *target, vt_map *synth, int stride, int max_rot, const float com[3], float *returncc,
+                      int bestrot[3], float *table);
+/* the map half of reset_density (TclVoltool.C:283-300); its atom half (:302-311) is vt_pose_apply */
+int vt_density_reset(vt_map *synth, int stride, const int bestrot[3], const float synthcom[3], const float com[3]);
+/* rotation x translation grid search (BASELINE cfg2's workload): candidate
+   ((ir * nt + ix) * nt + iy) * nt + iz, nt = 2 tsteps + 1, is rotation rot_deg[3 ir ..] about com followed by the
+   shift ((ix, iy, iz) - tsteps) * tstep (a vt_pose), scored by calc_cc (TclVoltool.C:73-129); the winner is the
+   first maximum in candidate order (`if (cc > best)`, :181; NaN never wins).  cc_all (may be NULL) receives every
+   score.  After vt_nccl_init rank r scores candidates r, r + world, ... and one ncclAllGather of the per-rank
+   (cc, index) merges them: every rank returns the same winner, cc_all holds NaN for other ranks' candidates. */
+int vt_fit_search_grid(vt_fit_ctx *ctx, const float com[3], const float *rot_deg, long nrot, int tsteps, float tstep,
+                       float *best_cc, long *best_index, vt_pose *best_pose, float *cc_all);
 
 /* multi-GPU: the pose search is the only sharded path.  rank r evaluates candidates r, r+world, ...
    and the per-stage tables are merged by the caller-supplied allgather (torch.distributed/NCCL in

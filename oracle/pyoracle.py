@@ -154,12 +154,46 @@ class Oracle:
         L.vo_value_interp_from_coord.restype = C.c_float
         L.vo_init_from_intersection.argtypes = [C.POINTER(Grid)] * 3
         L.vo_init_from_union.argtypes = [C.POINTER(Grid)] * 3
+        L.vo_cc_maps.argtypes = [C.POINTER(Grid), c_float_p, C.POINTER(Grid), c_float_p, C.c_double, c_double_p,
+                                 C.POINTER(Grid), C.POINTER(c_float_p), C.POINTER(Grid), C.POINTER(c_float_p)]
+        L.vo_density_rotate.argtypes = [C.c_int, C.c_int, c_float_p, c_float_p, C.POINTER(C.c_int), C.POINTER(Grid),
+                                        c_float_p, C.POINTER(Grid), c_float_p, c_float_p, C.c_int]
+        L.vo_density_rotate.restype = C.c_int
+        L.vo_density_reset.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(Grid), c_float_p, c_float_p, c_float_p]
 
     # ---- helpers -------------------------------------------------------------------------
     def _take(self, ptr, n):
         out = np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].copy()
         self.lib.vo_free(ptr)
         return out
+
+    # ---- cc extras / map-rotating search (restatements, see voltool_oracle.c) ------------------
+    def cc_maps(self, gA, a, gB, b, thr=-3.4028234663852886e38):
+        """(cc, diff grid, diff, spatial grid, spatial): TclMDFF.C:180-184, 555-594"""
+        a, b = f32(a), f32(b)
+        cc, dg, sg = C.c_double(), Grid(), Grid()
+        pd, ps = c_float_p(), c_float_p()
+        self.lib.vo_cc_maps(C.byref(gA), fp(a), C.byref(gB), fp(b), thr, C.byref(cc), C.byref(dg), C.byref(pd),
+                            C.byref(sg), C.byref(ps))
+        return cc.value, dg, self._take(pd, dg.n), sg, self._take(ps, sg.n)
+
+    def density_rotate(self, gA, a, gS, s, stride, max_rot, com, returncc=-1.0, nthreads=1):
+        """density_rotate, TclVoltool.C:202-279: (returncc, bestrot or None, table)"""
+        a, s, com = f32(a), f32(s), f32(com)
+        rc = C.c_float(returncc)
+        best = (C.c_int * 3)(-1, -1, -1)
+        tab = np.full(max_rot ** 3, np.nan, np.float32)
+        g2 = gS.copy()
+        self.lib.vo_density_rotate(stride, max_rot, fp(com), C.byref(rc), best, C.byref(gA), fp(a), C.byref(g2), fp(s),
+                                   fp(tab), nthreads)
+        return rc.value, (None if best[0] < 0 else tuple(best)), tab
+
+    def density_reset(self, gS, s, stride, bestrot, synthcom, com):
+        s, synthcom, com = f32(s), f32(synthcom), f32(com)
+        best = (C.c_int * 3)(*[int(v) for v in bestrot])
+        g2 = gS.copy()
+        self.lib.vo_density_reset(stride, best, C.byref(g2), fp(s), fp(synthcom), fp(com))
+        return g2
 
     # ---- CC --------------------------------------------------------------------------------
     def cc(self, gA, a, gB, b, thr=-3.4028234663852886e38, nthreads=1, full=False):

@@ -346,6 +346,85 @@ int vo_cc(const vo_grid *A, const float *a, const vo_grid *B, const float *b, do
 }
 
 /* ------------------------------------------------------------------------------------------
+ * `voltool cc -calcdiffmap / -calcspatialccmap` [RESTATEMENT, UNPINNED]
+ * usage TclMDFF.C:180-184, plumbing :555-594.  The maps come out of vmd_cuda_compare_sel_refmap
+ * (CUDAMDFF.cu), which is not in the snapshot; only their meaning is stated ("a difference map
+ * between the simulated and target densities", "a spatial map of the correlations between 8x8
+ * voxel regions").  Definition adopted here and by vt_cc_maps:
+ *   G        = init_from_intersection(A, B), the grid cc_threaded walks (MDFF.C:132)
+ *   a_i, b_i = the two interpolated samples of MDFF.C:70-71 at voxel i of G
+ *   diff[i]  = a_i - b_i on G (NaN where either sample is NaN)
+ *   tile t   = 8 x 8 x 8 voxels of G (ragged at the upper faces); its five sums and count run over
+ *              the voxels that pass MDFF.C:73-77, added in voxel order (x fastest) inside the tile
+ *   spatial[t] = the expression of MDFF.C:143-149 on the tile's sums; 0 for a tile without voxels
+ *   spatial grid: ceil(n/8) tiles per axis, origin of G, one cell = 8 cells of G
+ *   cc       = MDFF.C:143-149 on the tile sums added in tile order (x fastest): cc_threaded's value
+ *              up to the order of its double additions (which its threads do not fix either)
+ * ------------------------------------------------------------------------------------------ */
+static double cc_expr(const double s[5], long n) { /* MDFF.C:143-149 */
+  int size = (int)n;
+  double aMean = s[0] / size, bMean = s[1] / size;
+  double stdA = sqrt(s[2] / size - aMean * aMean);
+  double stdB = sqrt(s[3] / size - bMean * bMean);
+  return (s[4] - size * aMean * bMean) / (size * stdA * stdB);
+}
+
+void vo_spatial_grid(const vo_grid *G, vo_grid *sg) {
+  float xd[3], yd[3], zd[3];
+  vo_cell_axes(G, xd, yd, zd);
+  *sg = *G;
+  sg->xsize = (G->xsize + 7) / 8; sg->ysize = (G->ysize + 7) / 8; sg->zsize = (G->zsize + 7) / 8;
+  for (int k = 0; k < 3; k++) {
+    sg->xaxis[k] = 8.0 * (double)xd[k] * (double)(sg->xsize > 1 ? sg->xsize - 1 : 1);
+    sg->yaxis[k] = 8.0 * (double)yd[k] * (double)(sg->ysize > 1 ? sg->ysize - 1 : 1);
+    sg->zaxis[k] = 8.0 * (double)zd[k] * (double)(sg->zsize > 1 ? sg->zsize - 1 : 1);
+  }
+}
+
+int vo_cc_maps(const vo_grid *A, const float *a, const vo_grid *B, const float *b, double thr, double *cc,
+               vo_grid *dg, float **diff, vo_grid *sg, float **spatial) {
+  vo_grid nv;
+  vo_init_from_intersection(A, B, &nv);
+  *dg = nv;
+  vo_spatial_grid(&nv, sg);
+  long n = vo_gridsize(&nv), nt = vo_gridsize(sg);
+  float *d = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  float *sp = (float *)malloc(sizeof(float) * (size_t)(nt > 0 ? nt : 1));
+  float invA[16], invB[16];
+  vo_grid_inverse(A, 0, invA);
+  vo_grid_inverse(B, 0, invB);
+  double tot[5] = {0, 0, 0, 0, 0};
+  long ntot = 0;
+  for (int tz = 0; tz < sg->zsize; tz++)
+    for (int ty = 0; ty < sg->ysize; ty++)
+      for (int tx = 0; tx < sg->xsize; tx++) {
+        double s[5] = {0, 0, 0, 0, 0};
+        long cnt = 0;
+        for (int lz = 0; lz < 8 && tz * 8 + lz < nv.zsize; lz++)
+          for (int ly = 0; ly < 8 && ty * 8 + ly < nv.ysize; ly++)
+            for (int lx = 0; lx < 8 && tx * 8 + lx < nv.xsize; lx++) {
+              long i = ((long)(tz * 8 + lz) * nv.ysize + (ty * 8 + ly)) * nv.xsize + (tx * 8 + lx);
+              float x, y, z;
+              vo_voxel_coord(&nv, i, &x, &y, &z);
+              float vA = interp_from_coord_inv(A, a, invA, x, y, z, 0);
+              float vB = interp_from_coord_inv(B, b, invB, x, y, z, 0);
+              d[i] = vA - vB;
+              if (!vo_isnan(vB) && !vo_isnan(vA) && vA >= thr) {
+                s[0] += vA; s[1] += vB; s[2] += vA * vA; s[3] += vB * vB; s[4] += vA * vB;
+                cnt++;
+              }
+            }
+        sp[((long)tz * sg->ysize + ty) * sg->xsize + tx] = cnt > 0 ? (float)cc_expr(s, cnt) : 0.0f;
+        for (int k = 0; k < 5; k++) tot[k] += s[k];
+        ntot += cnt;
+      }
+  *cc = cc_expr(tot, ntot);
+  *diff = d;
+  *spatial = sp;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Two-map ops [PINNED]  Voltool.C:249-377
  * ------------------------------------------------------------------------------------------ */
 void vo_binary(int op, int interp, int use_union, const vo_grid *A, const float *a, const vo_grid *B,
@@ -1085,6 +1164,65 @@ int vo_rotate_replay(const float *cc_table, int max_rot, float *returncc, int *b
         }
       }
   return visited;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Map-rotating search [RESTATEMENT of dead code]  density_rotate TclVoltool.C:202-279, do_density_rotate
+ * :138-149, reset_density :281-311 (caller commented out, :820-891).  Per candidate (x, y, z): move the
+ * synthetic map's frame by -com (vol_moveto with pos = 0), rotate origin and axes about X, Y, Z
+ * (vol_move, Voltool.C:399-438), recompute its vol_com and move that back onto com, score
+ * cc_threaded(target, synth, 0.1) -- the TARGET is the thresholded map here (:252) -- and keep the
+ * best by `cc > *returncc` (no skip rule in this loop), then put the frame back.
+ * One deliberate deviation: the dead caller passes synthvol's OWN origin/axis arrays as the copies to
+ * restore from (:874-877), so its restore (:262-273) is a self-assignment and the rotations would pile
+ * up; this restatement restores from true copies taken on entry, which is what the loop is written to do.
+ * ------------------------------------------------------------------------------------------ */
+static void density_pose(vo_grid *S, const float *s, const float com[3], int stride, const int amt[3]) {
+  const float zero[3] = {0, 0, 0};
+  float m[16], currcom[3];
+  vo_vol_moveto(S, com, zero);                           /* :210 */
+  for (int ax = 0; ax < 3; ax++) {                       /* :212-222 */
+    double amount = (stride * amt[ax] * VO_PI / 180.0);  /* DEGTORAD, :141 */
+    vo_mat4_rot(m, ax, (float)amount);
+    vo_vol_move(S, m);
+  }
+  vo_vol_com(S, s, currcom);                             /* :225 */
+  vo_vol_moveto(S, currcom, com);                        /* :226 */
+}
+
+int vo_density_rotate(int stride, int max_rot, const float com[3], float *returncc, int bestrot[3], const vo_grid *A,
+                      const float *a, vo_grid *S, const float *s, float *cc_table, int nthreads) {
+  const vo_grid saved = *S;
+  int n = 0;
+  for (int x = 0; x < max_rot; x++)
+    for (int y = 0; y < max_rot; y++)
+      for (int z = 0; z < max_rot; z++) {
+        const int amt[3] = {x, y, z};
+        density_pose(S, s, com, stride, amt);
+        double ccd = 0.0;
+        vo_cc(A, a, S, s, 0.1, &ccd, 0, 0, nthreads);    /* density_calc_cc :66-71, :252 */
+        float cc = (float)ccd;
+        if (cc_table) cc_table[n] = cc;
+        n++;
+        if (cc > *returncc) { *returncc = cc; bestrot[0] = x; bestrot[1] = y; bestrot[2] = z; }   /* :254-261 */
+        *S = saved;                                      /* :262-273 */
+      }
+  return n;
+}
+
+/* the map half of reset_density (:283-300); the atom half (:302-311) is vo_pose_transform */
+void vo_density_reset(int stride, const int bestrot[3], vo_grid *S, const float *s, const float synthcom[3],
+                      const float com[3]) {
+  float move1[3] = {-1.0f * synthcom[0], -1.0f * synthcom[1], -1.0f * synthcom[2]};
+  float m[16], currcom[3];
+  vo_vol_moveto(S, synthcom, move1);                     /* :285 */
+  for (int ax = 0; ax < 3; ax++) {
+    double amount = (stride * bestrot[ax] * VO_PI / 180.0);
+    vo_mat4_rot(m, ax, (float)amount);
+    vo_vol_move(S, m);
+  }
+  vo_vol_com(S, s, currcom);                             /* :298 */
+  vo_vol_moveto(S, currcom, com);                        /* :299 */
 }
 
 /* literal rotate(): TclVoltool.C:151-200 */

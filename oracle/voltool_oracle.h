@@ -133,6 +133,18 @@ void vo_rotate_table(const float *origin_pos, const float *radii, long natoms, c
    returns number of candidates actually visited; best index in *best_idx (-1 = no update) */
 int vo_rotate_replay(const float *cc_table, int max_rot, float *returncc, int *best_idx);
 
+/* cc extras (TclMDFF.C:180-184, 555-594): diff map on the intersection grid + 8x8x8-tile spatial CC map
+   [RESTATEMENT, UNPINNED: definition in voltool_oracle.c].  *diff / *spatial are malloc()ed (vo_free). */
+void vo_spatial_grid(const vo_grid *G, vo_grid *sg);
+int vo_cc_maps(const vo_grid *A, const float *a, const vo_grid *B, const float *b, double thr, double *cc,
+               vo_grid *dg, float **diff, vo_grid *sg, float **spatial);
+/* density_rotate / reset_density (TclVoltool.C:202-311, dead code): the map-rotating search.  S's frame is
+   restored on return; cc_table (may be NULL) receives all max_rot^3 scores; returns the candidate count. */
+int vo_density_rotate(int stride, int max_rot, const float com[3], float *returncc, int bestrot[3], const vo_grid *A,
+                      const float *a, vo_grid *S, const float *s, float *cc_table, int nthreads);
+void vo_density_reset(int stride, const int bestrot[3], vo_grid *S, const float *s, const float synthcom[3],
+                      const float com[3]);
+
 typedef struct vo_fit_result {
   float best_cc;
   float com[3];

@@ -193,3 +193,69 @@ def test_vol_move_moveto_bit_exact(oracle, ref):
         a = 0.7
         mat = np.array([np.cos(a), np.sin(a), 0, 0, -np.sin(a), np.cos(a), 0, 0, 0, 0, 1, 0, 3.25, -1.5, 0.125, 1], np.float32)
         assert oracle.vol_move(g, mat).astuple() == ref.vol(g, d).move(mat).grid.astuple()
+
+
+def rot_mat(axis, angle_rad):
+    """Matrix4::rotate_axis for a unit axis (column-major), as the oracle restates it"""
+    c, s = np.float32(np.cos(np.float64(np.float32(angle_rad)))), np.float32(np.sin(np.float64(np.float32(angle_rad))))
+    m = np.eye(4, dtype=np.float32).reshape(-1)
+    if axis == 0:
+        m[5], m[6], m[9], m[10] = c, s, -s, c
+    elif axis == 1:
+        m[0], m[2], m[8], m[10] = c, -s, s, c
+    else:
+        m[0], m[1], m[4], m[5] = c, s, -s, c
+    return m
+
+
+def test_density_rotate_matches_reference_object_code(oracle, ref):
+    """density_rotate (TclVoltool.C:202-279) composed from the reference's OWN vol_moveto / vol_move / vol_com /
+    cc_threaded object code, candidate by candidate, against the oracle's restatement of the loop"""
+    gS = Grid.make((2.0, -1.0, 0.5), (13, 12, 11), 1.5)
+    gT = Grid.make((0.0, -3.0, -2.0), (24, 22, 20), 1.0)
+    s, t = rng_map(5, gS.n), rng_map(6, gT.n)
+    com = oracle.vol_com(gS, s)
+    stride, max_rot = 25, 3
+    cc_o, best_o, tab_o = oracle.density_rotate(gT, t, gS, s, stride, max_rot, com, -1.0)
+    vT = ref.vol(gT, t)
+    tab_r = []
+    for x in range(max_rot):
+        for y in range(max_rot):
+            for z in range(max_rot):
+                v = ref.vol(gS, s)
+                v.moveto(com, (0.0, 0.0, 0.0))
+                for ax, amt in enumerate((x, y, z)):
+                    v.move(rot_mat(ax, np.float32(stride * amt * np.pi / 180.0)))
+                v.moveto(v.com(), com)
+                tab_r.append(np.float32(ref.ref_cc_vols(vT, v, 0.1)))
+    tab_r = np.array(tab_r, np.float32)
+    assert np.array_equal(np.isnan(tab_o), np.isnan(tab_r))
+    ok = ~np.isnan(tab_r)
+    assert ok.sum() >= max_rot ** 3 // 2
+    assert np.max(np.abs(tab_o[ok] - tab_r[ok])) <= 1e-6      # float(cc); threaded double sums differ in order only
+    best = -1.0
+    bi = -1
+    for i, v in enumerate(tab_r):
+        if v > best:
+            best, bi = v, i
+    assert best_o == (bi // 9, (bi // 3) % 3, bi % 3)
+
+
+def test_cc_maps_twin_is_consistent(oracle):
+    """the diff / spatial-CC restatement: global value == cc_threaded's, diff == subtract on the intersection grid,
+    a tile's value == the CC of that tile cropped out"""
+    gs = grids()
+    for k, (gA, gB) in enumerate([(gs[0], gs[0]), (gs[1], gs[0]), (gs[2], gs[3])]):
+        a, b = rng_map(40 + k, gA.n), rng_map(50 + k, gB.n)
+        for thr in (-FLT_MAX, 0.3):
+            cc, dg, d, sg, sp = oracle.cc_maps(gA, a, gB, b, thr)
+            ref_cc = oracle.cc(gA, a, gB, b, thr)
+            assert (np.isnan(cc) and np.isnan(ref_cc)) or abs(cc - ref_cc) < 1e-10
+            assert same_grid(dg, oracle.intersection(gA, gB))
+            assert (sg.xsize, sg.ysize, sg.zsize) == ((dg.xsize + 7) // 8, (dg.ysize + 7) // 8, (dg.zsize + 7) // 8)
+            assert len(sp) == sg.n and np.all(np.abs(sp[~np.isnan(sp)]) <= 1.0 + 1e-6)
+        # interpolating subtract on the intersection grid is the same a - b where both samples exist
+        # (subtract uses the SAFE lookups: 0 outside instead of NaN)
+        og, sub = oracle.binary(1, gA, a, gB, b, interp=True, use_union=False)
+        inside = ~np.isnan(d)
+        assert np.array_equal(bits(sub[inside]), bits(d[inside]))

@@ -14,7 +14,8 @@ from .api import (Grid, Cache, Pose, FitResult, VolMap, VoltoolGpuError, lib, li
                   calc_cc, sim_cc, fit, FitContext, rotate_replay, pose_apply, measure_center, fit_schedule,
                   init_from_intersection, init_from_union, profile_enable, profile_reset, profile_get, write_dx,
                   read_dx, write_mrc, read_mrc, cc_host, binary_host, compact_selection, sim_sel, sim_cc_sel, fit_sel,
-                  nccl_unique_id, nccl_init, nccl_shutdown, best_pose_device, nccl_allgather)
+                  nccl_unique_id, nccl_init, nccl_shutdown, best_pose_device, nccl_allgather, cc_maps, sim_cc_maps,
+                  density_rotate, density_reset)
 
 __all__ = ["Grid", "Cache", "Pose", "FitResult", "VolMap", "VoltoolGpuError", "lib", "lib_path", "init", "shutdown",
            "sync", "launch_count", "device_props", "cc_threaded", "add", "subtract", "multiply", "average", "binary",
@@ -22,4 +23,4 @@ __all__ = ["Grid", "Cache", "Pose", "FitResult", "VolMap", "VoltoolGpuError", "l
            "measure_center", "fit_schedule", "init_from_intersection", "init_from_union", "profile_enable",
            "profile_reset", "profile_get", "write_dx", "read_dx", "write_mrc", "read_mrc", "cc_host", "binary_host",
            "compact_selection", "sim_sel", "sim_cc_sel", "fit_sel", "nccl_unique_id", "nccl_init", "nccl_shutdown",
-           "best_pose_device", "nccl_allgather"]
+           "best_pose_device", "nccl_allgather", "cc_maps", "sim_cc_maps", "density_rotate", "density_reset"]

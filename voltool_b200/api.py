@@ -184,6 +184,13 @@ def lib():
     L.vt_nccl_init.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.vt_fit_best_pose_device.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_void_p]
     L.vt_nccl_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+    L.vt_cc_maps.argtypes = [M, M, C.c_double, C.POINTER(C.c_double), C.POINTER(M), C.POINTER(M)]
+    L.vt_sim_cc_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_double, C.c_double, M, C.c_double,
+                                 C.POINTER(C.c_double), C.POINTER(M), C.POINTER(M), C.POINTER(M)]
+    L.vt_density_rotate.argtypes = [M, M, C.c_int, C.c_int, c_float_p, c_float_p, IP, C.c_void_p]
+    L.vt_density_reset.argtypes = [M, C.c_int, IP, c_float_p, c_float_p]
+    L.vt_fit_search_grid.argtypes = [C.c_void_p, c_float_p, C.c_void_p, C.c_long, C.c_int, C.c_float, c_float_p, LP,
+                                     C.POINTER(Pose), C.c_void_p]
     _lib = L
     return L
 
@@ -579,6 +586,47 @@ def sim_cc(pos, radii, resolution, target, threshold=-FLT_MAX, gspacing=0.0, wan
     return (cc.value, VolMap(_handle=h)) if want_synth else cc.value
 
 
+def cc_maps(map_a, map_b, threshold=-FLT_MAX, want_diff=True, want_spatial=True):
+    """cc + the -calcdiffmap / -calcspatialccmap outputs (TclMDFF.C:180-184, 555-594): (cc, diff, spatial)"""
+    _need()
+    cc, hd, hs = C.c_double(), C.c_void_p(), C.c_void_p()
+    _check(lib().vt_cc_maps(map_a.h, map_b.h, threshold, C.byref(cc), C.byref(hd) if want_diff else None,
+                            C.byref(hs) if want_spatial else None), "vt_cc_maps")
+    return cc.value, (VolMap(_handle=hd) if want_diff else None), (VolMap(_handle=hs) if want_spatial else None)
+
+
+def sim_cc_maps(pos, radii, resolution, target, threshold=-FLT_MAX, gspacing=0.0):
+    """mdff_cc with -calcsynthmap -calcdiffmap -calcspatialccmap: (cc, synth, diff, spatial)"""
+    _need()
+    pos, radii = f32(pos).reshape(-1), f32(radii).reshape(-1)
+    cc, h0, h1, h2 = C.c_double(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _check(lib().vt_sim_cc_maps(_vp(pos), _vp(radii), radii.size, resolution, gspacing, target.h, threshold,
+                                C.byref(cc), C.byref(h0), C.byref(h1), C.byref(h2)), "vt_sim_cc_maps")
+    return cc.value, VolMap(_handle=h0), VolMap(_handle=h1), VolMap(_handle=h2)
+
+
+def density_rotate(target, synth, stride, max_rot, com, returncc=-1.0):
+    """density_rotate, TclVoltool.C:202-279: (returncc, bestrot or None, table of all max_rot^3 scores)"""
+    _need()
+    cp, keep = _fp3(com)
+    rc_ = C.c_float(returncc)
+    best = (C.c_int * 3)(-1, -1, -1)
+    tab = np.full(max_rot ** 3, np.nan, np.float32)
+    _check(lib().vt_density_rotate(target.h, synth.h, stride, max_rot, cp, C.byref(rc_), best, _vp(tab)),
+           "vt_density_rotate")
+    return rc_.value, (None if best[0] < 0 else tuple(best)), tab
+
+
+def density_reset(synth, stride, bestrot, synthcom, com):
+    """the map half of reset_density, TclVoltool.C:283-300"""
+    _need()
+    a, ka = _fp3(synthcom)
+    b, kb = _fp3(com)
+    best = (C.c_int * 3)(*[int(v) for v in bestrot])
+    _check(lib().vt_density_reset(synth.h, stride, best, a, b), "vt_density_reset")
+    return synth
+
+
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
 
@@ -721,6 +769,18 @@ class FitContext:
         cp, keep = _fp3(com)
         _check(lib().vt_fit_eval_poses_device(self.h, cp, C.c_void_p(d_poses_ptr), nposes, C.c_void_p(d_cc_ptr)),
                "vt_fit_eval_poses_device")
+
+    def search_grid(self, com, rot_deg, tsteps, tstep, want_all=False):
+        """rotation x translation grid search (vt_fit_search_grid): (best_cc, best_index, best_pose(6,), cc_all)"""
+        rot = f32(rot_deg).reshape(-1, 3)
+        nt = 2 * tsteps + 1
+        allcc = np.empty(len(rot) * nt ** 3, np.float32) if want_all else None
+        cp, keep = _fp3(com)
+        bcc, bidx, bpose = C.c_float(), C.c_long(), Pose()
+        _check(lib().vt_fit_search_grid(self.h, cp, _vp(rot), len(rot), tsteps, tstep, C.byref(bcc), C.byref(bidx),
+                                        C.byref(bpose), _vp(allcc) if want_all else None), "vt_fit_search_grid")
+        pose = np.array(list(bpose.rot_deg) + list(bpose.shift), np.float32)
+        return bcc.value, bidx.value, pose, allcc
 
     def rotate_table(self, com, stride, max_rot, first=0, step=1):
         tab = np.full(max_rot ** 3, np.nan, np.float32)

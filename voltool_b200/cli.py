@@ -23,14 +23,15 @@ two-map commands (-i1 <a.dx> -i2 <b.dx>):
   correlate [-thresholddensity x]
 atom commands (-atoms <table: x y z radius [mass]> -res R):
   sim [-spacing g] [-o <out.dx>]
-  cc  -i <target.dx> [-spacing g] [-thresholddensity x] [-savesynthmap <out.dx>]
+  cc  -i <target.dx> [-spacing g] [-thresholddensity x] [-savesynthmap <out.dx>] [-savediffmap <out.dx>]
+      [-savespatialccmap <out.dx>]
   fit -i <target.dx> [-o <fitted atoms table>]
 """
 
 # how many values each option takes (0 = flag); list options accept one quoted word or that many words
 NARGS = {"-i": 1, "-o": 1, "-i1": 1, "-i2": 1, "-atoms": 1, "-res": 1, "-spacing": 1, "-sigma": 1, "-amt": -1,
          "-minmax": 2, "-min": 1, "-max": 1, "-threshold": 1, "-nbins": 1, "-pos": 3, "-mat": 16,
-         "-thresholddensity": 1, "-savesynthmap": 1, "-union": 0, "-nointerp": 0}
+         "-thresholddensity": 1, "-savesynthmap": 1, "-savediffmap": 1, "-savespatialccmap": 1, "-union": 0, "-nointerp": 0}
 AMT_LEN = {"trim": 6, "crop": 6, "smult": 1, "sadd": 1}
 
 
@@ -207,6 +208,13 @@ def run(cmd, o, pos):
         target = load()
         if cmd == "cc":
             thr = float(o.get("-thresholddensity", -FLT_MAX))            # TclMDFF.C:216
+            if "-savediffmap" in o or "-savespatialccmap" in o:           # -calcdiffmap / -calcspatialccmap, :180-184
+                cc, synth, diff, spat = vt.sim_cc_maps(apos, radii, res, target, thr, gs)
+                for key, m in (("-savesynthmap", synth), ("-savediffmap", diff), ("-savespatialccmap", spat)):
+                    if key in o:
+                        m.write_file(o[key])
+                print("%.9g" % cc)
+                return 0
             want = "-savesynthmap" in o
             r = vt.sim_cc(apos, radii, res, target, thr, gs, want_synth=want)
             if want:
