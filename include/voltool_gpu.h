@@ -69,6 +69,9 @@ void *vt_stream(void);
 int vt_map_create(const vt_grid *g, const float *host_data, vt_map **out);
 /* as above from a DEVICE pointer (device-to-device copy) */
 int vt_map_create_from_device(const vt_grid *g, const float *dev_data, vt_map **out);
+/* the twin of an EXISTING VolumetricData (shim/VolumetricDataGPU.C): uploads its voxels and takes its
+   cached-statistics block as it stands instead of recomputing it */
+int vt_map_adopt_host(const vt_grid *g, const float *host_data, const vt_cache *cache, vt_map **out);
 int vt_map_clone(const vt_map *m, vt_map **out);
 int vt_map_destroy(vt_map *m); /* VolumetricData::~VolumetricData, VolumetricData.C:93-99 */
 int vt_map_grid(const vt_map *m, vt_grid *g);

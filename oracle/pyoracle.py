@@ -398,10 +398,12 @@ class Ref(Oracle):
     OPS = {"clamp": 0, "scale_by": 1, "scalar_add": 2, "rescale_range": 3, "sigma_scale": 4, "binmask": 5,
            "mdff_potential": 6, "downsample": 7, "supersample": 8, "blur": 9, "pad": 10, "crop": 11}
 
-    def __init__(self):
-        if not os.path.exists(self.LIB):
+    def __init__(self, path=None):
+        """path: another library with the same flat API over the reference's classes -- the compiled adapter
+        shim/_build/libvoltool_shim.so runs the SAME VolumetricData class with GPU bodies"""
+        if path is None and not os.path.exists(self.LIB):
             build(ref=True)
-        super().__init__(self.LIB)
+        super().__init__(path or self.LIB)
         L = self.lib
         L.ref_vol_new.argtypes = [C.POINTER(Grid), c_float_p]
         L.ref_vol_new.restype = C.c_void_p

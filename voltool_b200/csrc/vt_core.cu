@@ -199,6 +199,19 @@ int vt_map_create(const vt_grid *g, const float *host, vt_map **out) {
   return map_compute_minmax(m);
 }
 
+// the resident twin of an EXISTING VolumetricData: its voxels and its cached-statistics block as they stand
+// (no compute_minmax: the object was constructed long ago and its caches carry history, VolumetricData.h:202-210)
+int vt_map_adopt_host(const vt_grid *g, const float *host, const vt_cache *cache, vt_map **out) {
+  VT_REQUIRE_CTX();
+  if (!host || !cache) { set_error("vt_map_adopt_host: null argument"); return 1; }
+  int rc = map_alloc(g, out);
+  if (rc) return rc;
+  vt_map *m = *out;
+  m->cache = *cache;
+  if (m->n > 0) VT_CUDA(cudaMemcpyAsync(m->d, host, sizeof(float) * (size_t)m->n, cudaMemcpyHostToDevice, ctx().stream));
+  return 0;
+}
+
 int vt_map_create_from_device(const vt_grid *g, const float *dev, vt_map **out) {
   VT_REQUIRE_CTX();
   int rc = map_alloc(g, out);
