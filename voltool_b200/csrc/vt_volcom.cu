@@ -87,19 +87,27 @@ __global__ void __launch_bounds__(96) com_tables_kernel(const float *__restrict_
   }
 }
 
-// pass 2: one CTA of 8 warps.  Lanes 0..2 of warp 0 own the accumulators and take the O(1) table
-// step when they can; when any of them has to replay a chunk, all 256 threads first rebuild that
-// chunk's addends in shared memory (coalesced loads, parallel coordinate arithmetic) and the owning
-// lane then does only the dependent float adds.
+// pass 2: one CTA of 8 warps.  Lanes 0..2 of warp 0 own the accumulators and take the O(1) table step when they
+// can.  The walk is a chain of dependent steps, so what matters is the latency of one step: the table entries of
+// the next kWalkBlock chunks are fetched by all 256 threads at once into shared memory -- for the binade each
+// accumulator is in when the block starts, which is the right one unless the sum crosses a binade inside the block
+// (then that step reads global memory, as every step used to).  When an accumulator has to replay a chunk, all 256
+// threads first rebuild that chunk's addends in shared memory (coalesced loads, parallel coordinate arithmetic) and
+// the owning lane then does only the dependent float adds.
 constexpr int kWalkThreads = 256;
+constexpr int kWalkBlock = 256;   // chunks per prefetch (one per thread)
+constexpr unsigned int kCmdExit = 0xffffffffu, kCmdPrefetch = 0xfffffffeu;
 
 __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__restrict__ d, long n, DevCoord c, int L,
                                                                long nchunks, const ComEntry *__restrict__ tab,
                                                                const int *__restrict__ emin, float *__restrict__ out,
                                                                int *__restrict__ replayed) {
   extern __shared__ float s_a[];  // [3][L]
-  __shared__ unsigned int s_need;   // which accumulators replay the chunk in s_chunk (0xffffffff: exit)
-  __shared__ long s_chunk;
+  __shared__ unsigned int s_need;   // accumulators that replay the chunk in s_chunk, or a command
+  __shared__ long s_chunk;          // chunk to replay / first chunk of the block to prefetch
+  __shared__ int s_snap[3];         // exponent bits of each accumulator when the block was prefetched
+  __shared__ int s_e0[3][kWalkBlock];
+  __shared__ long long s_T[3][kWalkBlock], s_A2[3][kWalkBlock];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long nxy = (long)c.nx * c.ny;
 
@@ -118,15 +126,30 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
         if ((need >> kk) & 1) s_a[kk * L + i] = com_addend(c, kk, m, gx, gy, gz);
     }
   };
+  // all threads: thread t fetches chunk first + t's window start and its table entry for the snapshot binades
+  auto prefetch = [&](long first) {
+    const long chunk = first + tid;
+    if (chunk < nchunks) {
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) {
+        const int e0 = emin[chunk * 3 + kk];
+        const int j = (s_snap[kk] - 127) - e0;
+        ComEntry en;
+        en.T = 0; en.A2 = 0;
+        if (e0 > -100000 && e0 < 100000 && j >= 0 && j < kBinades) en = tab[(chunk * 3 + kk) * kBinades + j];
+        s_e0[kk][tid] = e0; s_T[kk][tid] = en.T; s_A2[kk][tid] = en.A2;
+      }
+    }
+  };
 
   if (warp != 0) {
-    // helper warps sleep on barrier 1 until warp 0 posts a chunk to replay (or the exit command);
-    // the table fast path of warp 0 involves no barrier at all
+    // helper warps sleep on barrier 1 until warp 0 posts a command; the table fast path of warp 0 involves no barrier
     while (true) {
       asm volatile("bar.sync 1, %0;" ::"r"(kWalkThreads));
       const unsigned int need = s_need;
-      if (need == 0xffffffffu) break;
-      stage(s_chunk, need);
+      if (need == kCmdExit) break;
+      if (need == kCmdPrefetch) prefetch(s_chunk);
+      else stage(s_chunk, need);
       asm volatile("bar.sync 2, %0;" ::"r"(kWalkThreads));
     }
     return;
@@ -136,10 +159,73 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
   const int k = owner ? lane : 0;
   float s = 0.0f;
   int nreplay = 0;
+  int snap = 0;
+  bool skip = false;   // this accumulator already jumped the current group of 32 chunks
   for (long chunk = 0; chunk < nchunks; ++chunk) {
+    const int t = (int)(chunk % kWalkBlock);
+    if (t == 0) {
+      snap = (int)((__float_as_uint(s) >> 23) & 0xff);
+      if (owner) s_snap[k] = snap;
+      if (lane == 0) { s_need = kCmdPrefetch; s_chunk = chunk; }
+      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"r"(kWalkThreads));
+      prefetch(chunk);
+      asm volatile("bar.sync 2, %0;" ::"r"(kWalkThreads));
+    }
+    // 32 chunks in one step: within a binade the table step is the integer addition S <- S + T, so a warp scan of
+    // the T's gives every intermediate sum at once and each chunk's validity test (the sum stays inside the binade,
+    // no tie, a usable table entry) is checked against its own prefix.  If all 32 hold the accumulator jumps the
+    // whole group; otherwise that accumulator walks the group chunk by chunk below.
+    if ((t & 31) == 0) {
+      skip = false;
+      if (chunk + 32 <= nchunks) {
+        int npass = 0;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          const unsigned int bits = __float_as_uint(__shfl_sync(0xffffffffu, s, kk));
+          const int ebits = (int)((bits >> 23) & 0xff);
+          const int snap_k = __shfl_sync(0xffffffffu, snap, kk);
+          const long long S = (long long)(bits & 0x7fffffu) | 0x800000ll;
+          const long long Ss = (bits >> 31) ? -S : S;
+          const int e0 = s_e0[kk][t + lane];
+          long long T = 0, A = 0;
+          bool ok = ebits != 0 && ebits != 0xff && ebits == snap_k;
+          if (e0 != -100000) {
+            const int j = (ebits - 127) - e0;
+            if (e0 >= 100000 || j < 0) ok = false;
+            else if (j < kBinades) {
+              const long long a2 = s_A2[kk][t + lane];
+              T = s_T[kk][t + lane]; A = a2 >> 1;
+              if (a2 & 1) ok = false;
+            }
+          }
+          long long P = T;   // inclusive prefix of T over the group
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, P, o);
+            if (lane >= o) P += v;
+          }
+          const long long before = Ss + P - T;
+          const long long lo = before - A, hi = before + A;
+          const bool inside = Ss > 0 ? (lo >= 0x800001ll && hi <= 0xfffffell) : (hi <= -0x800001ll && lo >= -0xfffffell);
+          // (a chunk without addends, e0 == -100000, changes nothing wherever the sum stands)
+          const bool pass = __all_sync(0xffffffffu, ok && (inside || e0 == -100000));
+          const long long R = Ss + __shfl_sync(0xffffffffu, P, 31);
+          if (pass) {
+            ++npass;
+            if (lane == kk) {
+              const long long Ra = R < 0 ? -R : R;
+              s = __uint_as_float((R < 0 ? 0x80000000u : 0u) | ((unsigned int)ebits << 23) | (unsigned int)(Ra & 0x7fffffll));
+              skip = true;
+            }
+          }
+        }
+        if (npass == 3) { chunk += 31; continue; }
+      }
+    }
     bool replay = false;
-    if (owner) {
-      const int e0 = emin[chunk * 3 + k];
+    if (owner && !skip) {
+      const int e0 = s_e0[k][t];
       if (e0 != -100000) {  // else: nothing to add
         replay = true;
         const unsigned int bits = __float_as_uint(s);
@@ -153,7 +239,9 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
           bool have = false;
           if (j >= kBinades) { have = true; }                // every addend rounds to zero
           else if (j >= 0) {
-            const ComEntry en = tab[(chunk * 3 + k) * kBinades + j];
+            ComEntry en;
+            if (ebits == snap) { en.T = s_T[k][t]; en.A2 = s_A2[k][t]; }
+            else en = tab[(chunk * 3 + k) * kBinades + j];   // the sum left the prefetched binade inside this block
             T = en.T; A = en.A2 >> 1; tie = (int)(en.A2 & 1); have = true;
           }
           if (have && !tie) {
@@ -196,7 +284,7 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
     }
     __syncwarp();
   }
-  if (lane == 0) s_need = 0xffffffffu;
+  if (lane == 0) s_need = kCmdExit;
   __syncwarp();
   asm volatile("bar.sync 1, %0;" ::"r"(kWalkThreads));
   if (owner) {
