@@ -146,6 +146,51 @@ def test_cc_identity_stream_path(oracle, monkeypatch):
                     assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (poison, which, got, want)
 
 
+def test_cc_identity_poison_bordering_the_overlap(oracle, monkeypatch):
+    """the reference's sample of a box voxel reads its +1 neighbours: a NaN / inf / huge voxel of the LARGER map just
+    beyond the common box's upper faces must reach the result although the streamed box never contains it"""
+    A = OGrid.make((0, 0, 0), (40, 36, 32), 1.0)
+    B = OGrid.make((-4, -8, -2), (64, 60, 56), 1.0)         # A is an aligned sub-box of B, ending inside it
+    r = np.random.default_rng(14)
+    a, b = r.random(A.n, dtype=np.float32), r.random(B.n, dtype=np.float32)
+    og = oracle.intersection(A, B)
+    ox, oy, oz = og.xsize, og.ysize, og.zsize
+    bz, by, bx = B.shape
+    b3 = b.reshape(bz, by, bx)
+    monkeypatch.setenv("VOLTOOL_CC_IDENTITY", "1")
+    for poison in (np.nan, np.inf, 3.0e38):
+        for where in ((2 + oz, 8 + 5, 4 + 7), (2 + 3, 8 + oy, 4 + 9), (2 + 6, 8 + 11, 4 + ox), (2 + oz, 8 + oy, 4 + ox)):
+            b2 = b3.copy()
+            b2[where] = poison                                # one voxel past the box on the +z / +y / +x face / the corner
+            want, nw, _ = oracle.cc(A, a, B, b2.reshape(-1), -FLT_MAX, full=True)
+            got, ng, _ = vt.cc_threaded(vt.VolMap(G(A), a), vt.VolMap(G(B), b2.reshape(-1)), -FLT_MAX, full=True)
+            assert ng == nw, (poison, where)
+            assert (np.isnan(want) and np.isnan(got)) or abs(got - want) <= 1e-9 * max(1.0, abs(want)), (poison, where, got, want)
+            for op in (0, 2):                                 # and the two-map ops (bit-exact)
+                gw, want_o = oracle.binary(op, A, a, B, b2.reshape(-1), True, False)
+                got_o = vt.binary(op, vt.VolMap(G(A), a), vt.VolMap(G(B), b2.reshape(-1)), True, False)
+                assert np.array_equal(bits(got_o.data), bits(want_o)), (op, poison, where)
+
+
+def test_cc_identity_low_variance_tolerance(oracle, monkeypatch):
+    """the streaming kernel adds each group of four voxel terms in float before promoting to double (MDFF.C:79-83
+    promotes every term); on maps whose variance is small against their mean the cancellation in
+    sumAA/n - mean^2 amplifies that.  Stated tolerance: 1e-5 on CC (north star) down to sd/mean = 1e-2."""
+    g = OGrid.make((0, 0, 0), (64, 60, 56), 1.0)
+    r = np.random.default_rng(15)
+    for rel in (1e-1, 1e-2):
+        a = (10.0 * (1.0 + rel * r.standard_normal(g.n))).astype(np.float32)
+        b = (0.6 * a + 4.0 * (1.0 + rel * r.standard_normal(g.n))).astype(np.float32)
+        want = oracle.cc(g, a, g, b)
+        monkeypatch.setenv("VOLTOOL_CC_IDENTITY", "1")
+        got = vt.cc_threaded(vt.VolMap(G(g), a), vt.VolMap(G(g), b))
+        monkeypatch.setenv("VOLTOOL_CC_IDENTITY", "0")
+        ref = vt.cc_threaded(vt.VolMap(G(g), a), vt.VolMap(G(g), b))
+        monkeypatch.delenv("VOLTOOL_CC_IDENTITY")
+        assert abs(ref - want) <= 1e-9
+        assert abs(got - want) <= 1e-5 * abs(want), (rel, got, want)
+
+
 def test_cc_known_answers():
     g = vt.Grid.make((0, 0, 0), (64, 60, 56), 1.0)
     a = rng_map(5, g.n)

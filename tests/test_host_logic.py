@@ -322,6 +322,13 @@ def test_mrc_modes_axis_order_and_byte_order(tmp_path):
             f.write(_mrc_header(4, 3, 2, mode, origin=(5.0, 6.0, 7.0)) + v.tobytes())
         g2, d2 = vt.read_mrc(p2)
         assert np.array_equal(d2, v.astype(np.float32).reshape(-1)) and tuple(g2.origin) == (5.0, 6.0, 7.0)
+    # both ORIGIN and NSTART set: the ORIGIN words win, the shift is not applied twice
+    both = str(tmp_path / "both.mrc")
+    v = np.arange(24, dtype="<f4").reshape(2, 3, 4)
+    with open(both, "wb") as f:
+        f.write(_mrc_header(4, 3, 2, 2, start=(3, -2, 1), origin=(5.0, 6.0, 7.0)) + v.tobytes())
+    gb, _ = vt.read_mrc(both)
+    assert tuple(gb.origin) == (5.0, 6.0, 7.0)
     # errors: truncated data, unsupported mode, non-orthogonal cell
     bad = str(tmp_path / "bad.mrc")
     with open(bad, "wb") as f:

@@ -221,10 +221,11 @@ int vt_histogram(vt_map *m, int nbins, long *bins, float *midpts) {
   unsigned long long *d_bins;
   if (dev_alloc((void **)&d_bins, sizeof(unsigned long long) * nbins)) return 2;
   rc = k_histogram(m->d, m->n, mn, binwidthinv, nbins, d_bins);
-  if (rc) return rc;
+  if (rc) { dev_free(d_bins); return rc; }
   unsigned long long *h = (unsigned long long *)malloc(sizeof(unsigned long long) * nbins);
-  VT_CUDA(cudaMemcpyAsync(h, d_bins, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, ctx().stream));
-  VT_CUDA(cudaStreamSynchronize(ctx().stream));
+  cudaError_t e = cudaMemcpyAsync(h, d_bins, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, ctx().stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+  if (e != cudaSuccess) { free(h); dev_free(d_bins); return cuda_fail(e, "vt_histogram readback", __FILE__, __LINE__); }
   for (int j = 0; j < nbins; ++j) {
     bins[j] = (long)h[j];
     midpts[j] = (float)(mn + (0.5 * binwidth) + (j * binwidth));      // Voltool.C:458
@@ -244,7 +245,7 @@ int vt_pad(vt_map *m, int pxm, int pxp, int pym, int pyp, int pzm, int pzp) {
   float *fresh;
   if (dev_alloc((void **)&fresh, sizeof(float) * (size_t)gridsize(g))) return 2;
   int rc = k_pad_copy(m->d, ox, oy, fresh, p);
-  if (rc) return rc;
+  if (rc) { dev_free(fresh); return rc; }
   return replace_data(m, fresh, g);
 }
 
@@ -286,10 +287,10 @@ int vt_gaussian_blur(vt_map *m, double sigma) {
   if (R >= 0 && m->n > 0) {
     float *fresh, *tmp;
     if (dev_alloc((void **)&fresh, sizeof(float) * (size_t)m->n)) return 2;
-    if (dev_alloc((void **)&tmp, sizeof(float) * (size_t)m->n)) return 2;
+    if (dev_alloc((void **)&tmp, sizeof(float) * (size_t)m->n)) { dev_free(fresh); return 2; }
     int rc = k_blur(m->d, fresh, tmp, m->grid.xsize, m->grid.ysize, m->grid.zsize, w, R);
     dev_free(tmp);
-    if (rc) return rc;
+    if (rc) { dev_free(fresh); return rc; }
     return replace_data(m, fresh, m->grid);
   }
   // sigma <= 0: data unchanged, caches still dropped (VolumetricData.C:990-996)

@@ -13,6 +13,7 @@
 //             and the inner loop is table-driven.  Threads run along x and march in z, reusing
 //             the bilinear value of the shared plane between consecutive z steps when the index
 //             advances by one.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -221,6 +222,40 @@ static bool identity_tables(const std::vector<AxisEntry> &tab, const int off[6],
   return true;
 }
 
+// The reference's sample of a box voxel also reads its +1 neighbours (a0 + 0*(a1-a0), VolumetricData.C:273-287):
+// where the common box stops short of a map's upper face those neighbours lie OUTSIDE the box the identity
+// kernels stream, and a NaN / inf / huge value there poisons the reference's sample all the same.  One-voxel-thick
+// slabs just beyond the box's upper faces (edges and the corner included) are scanned for such values here.
+__global__ void __launch_bounds__(kThreads) face_bad_kernel(const float *__restrict__ d, long row, long plane, int x0, int nxs,
+                                                            int y0, int nys, int z0, int nzs, int *bad_out) {
+  const long n = (long)nxs * nys * nzs;
+  bool bad = false;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % nxs), y = (int)((i / nxs) % nys), z = (int)(i / ((long)nxs * nys));
+    const float v = d[(long)(z0 + z) * plane + (long)(y0 + y) * row + (x0 + x)];
+    bad = bad || !(fabsf(v) < 8.0e37f);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(bad_out, 1);
+}
+
+static int scan_plus_faces(const DevMap &m, const int shift[3], const int nout[3], int *d_bad) {
+  Ctx &c = ctx();
+  const int nsrc[3] = {m.nx, m.ny, m.nz};
+  int ext[3];
+  for (int ax = 0; ax < 3; ++ax) ext[ax] = shift[ax] + nout[ax] < nsrc[ax] ? 1 : 0;   // a +1 neighbour exists beyond the box
+  for (int ax = 0; ax < 3; ++ax) {
+    if (!ext[ax]) continue;
+    int lo[3], len[3];
+    for (int k = 0; k < 3; ++k) { lo[k] = shift[k]; len[k] = nout[k] + ext[k]; }
+    lo[ax] = shift[ax] + nout[ax]; len[ax] = 1;
+    const long n = (long)len[0] * len[1] * len[2];
+    const int grid = (int)std::min<long>((n + kThreads - 1) / kThreads, (long)c.sm_count * 4);
+    face_bad_kernel<<<grid, kThreads, 0, c.stream>>>(m.d, m.nx, (long)m.nx * m.ny, lo[0], len[0], lo[1], len[1], lo[2], len[2], d_bad);
+    VT_LAUNCHED();
+  }
+  return 0;
+}
+
 constexpr int kZChunk = 32;  // output z steps per warp work item
 
 __global__ void __launch_bounds__(kThreads, 2) cc_sep_kernel(DevMap A, DevMap B, int nx, int ny, int nz, int zchunk,
@@ -302,6 +337,8 @@ int k_cc(const vt_map *A, const vt_map *B, double thr, double sums[5], long *n) 
       VT_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c.stream));
       const long wblocks = ((long)og.ysize * og.zsize + kThreads / 32 - 1) / (kThreads / 32);
       const int grid = (int)(wblocks < (long)c.sm_count * 8 ? wblocks : (long)c.sm_count * 8);
+      if (int frc = scan_plus_faces(dA, shift[0], nout, d_bad)) return frc;
+      if (int frc = scan_plus_faces(dB, shift[1], nout, d_bad)) return frc;
       prof_begin(PK_CC);
       if (vec) cc_identity_kernel<true><<<grid, kThreads, 0, c.stream>>>(ia, threshold_as_float(thr), partials, c.d_ticket, dout, d_bad);
       else cc_identity_kernel<false><<<grid, kThreads, 0, c.stream>>>(ia, threshold_as_float(thr), partials, c.d_ticket, dout, d_bad);
@@ -543,6 +580,8 @@ int k_binary(int op, int interp, int use_union, const vt_map *A, const vt_map *B
                        ((uintptr_t)ia.b % 16 == 0) && ((uintptr_t)out % 16 == 0);
       int *d_bad = reinterpret_cast<int *>(c.d_scratch);
       VT_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c.stream));
+      if (int frc = scan_plus_faces(dA, shift[0], nout, d_bad)) return frc;
+      if (int frc = scan_plus_faces(dB, shift[1], nout, d_bad)) return frc;
       switch (mode) {
         case 1: launch_binary_identity<1>(ia, vec, out, dA, dB, dC, d_bad); break;
         case 2: launch_binary_identity<2>(ia, vec, out, dA, dB, dC, d_bad); break;

@@ -274,8 +274,11 @@ int vt_mrc_read(const char *path, vt_grid *g, float **data_out) {
   const float org[4] = {0.f, h.f(50), h.f(51), h.f(52)};
   const int nxyz[4] = {0, nx, ny, nz};
   double *axis[4] = {nullptr, g->xaxis, g->yaxis, g->zaxis};
+  // the origin is the ORIGIN words (MRC2014) when any of them is set, else the N*START offsets of the older CCP4
+  // convention -- never both (files that carry both describe the same shift twice)
+  const bool has_origin = org[1] != 0.f || org[2] != 0.f || org[3] != 0.f;
   for (int a = 1; a <= 3; ++a) {
-    g->origin[a - 1] = (double)org[a] + (double)start_of[a] * vox[a];
+    g->origin[a - 1] = has_origin ? (double)org[a] : (double)start_of[a] * vox[a];
     axis[a][a - 1] = vox[a] * (nxyz[a] > 1 ? nxyz[a] - 1 : 1);
   }
   g->xsize = nx; g->ysize = ny; g->zsize = nz;

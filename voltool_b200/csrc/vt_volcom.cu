@@ -312,6 +312,11 @@ int k_vol_com(const vt_map *m, double out[4]) {
   ComEntry *tab = nullptr;
   int *emin = nullptr;
   float *d_out = nullptr;
+  // (every exit below releases all three: the pool never hands blocks back by itself)
+  struct Scratch {
+    ComEntry *&tab; int *&emin; float *&d_out;
+    ~Scratch() { dev_free(tab); dev_free(emin); dev_free(d_out); }
+  } scratch{tab, emin, d_out};
   if (dev_alloc((void **)&tab, sizeof(ComEntry) * (size_t)nchunks * 3 * kBinades)) return 2;
   if (dev_alloc((void **)&emin, sizeof(int) * (size_t)nchunks * 3)) return 2;
   if (dev_alloc((void **)&d_out, sizeof(float) * 8)) return 2;
@@ -329,7 +334,6 @@ int k_vol_com(const vt_map *m, double out[4]) {
   float h[8];
   VT_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
   VT_CUDA(cudaStreamSynchronize(c.stream));
-  dev_free(tab); dev_free(emin); dev_free(d_out);
   for (int k = 0; k < 3; ++k) out[k] = (double)h[k];
   double mass = 0.0;
   int rc = k_sum(m->d, n, &mass);
