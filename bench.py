@@ -335,6 +335,30 @@ def run_ours(args):
                                      if world > 1 else "none (one rank)",
                        "note": "whole vt_fit call incl. vol_com of the 256^3 target and the workspace set-up; max over ranks, best of 3"}
 
+    # ---- cfg5's "fit with local rigid refinement on N GPUs": every rank holds the 250k-atom structure and the ~400^3
+    # target; each refinement stage is sharded by the library and merged with one ncclAllGather of (cc, index)
+    cfg5_sharded = None
+    if world > 1 and not args.no_extras and args.cfg5_atoms > 0:
+        from voltool_b200.synth import make_structure
+        ball = 105.0 * (args.cfg5_atoms / 250000.0) ** (1 / 3)
+        p5, r5, m5 = make_structure(args.cfg5_atoms, ball, seed=5001, center=(ball + 12.0,) * 3)
+        rs5, _, q5 = vt.sim_policy(3.0)
+        barrier()
+        refine, ctx5 = cfg5_refine(vt, p5, r5, m5, q5, rs5, (2.0 * ball + 8.0) / args.cfg5_edge)
+        ctx5.close()
+        tt = torch.tensor([refine["seconds"]], device="cuda", dtype=torch.float64)
+        sig = torch.tensor(refine["best_deg"] + [refine["best_cc"]], device="cuda", dtype=torch.float64)
+        sig_all = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_gather(sig_all, sig)
+        refine["seconds"] = float(tt[0].item())
+        refine["poses_per_s"] = refine["poses"] / refine["seconds"]
+        refine["ranks"] = world
+        refine["all_ranks_same_pose"] = all(bool(torch.equal(x, sig_all[0])) for x in sig_all)
+        refine["collective"] = "ncclAllGather of the per-rank (cc, index), one per stage"
+        cfg5_sharded = refine
+        del p5, r5, m5
+
     if rank != 0:
         if world > 1:
             vt.nccl_shutdown()
@@ -376,6 +400,8 @@ def run_ours(args):
 
     if fit_sharded is not None:
         out["fit_call"] = fit_sharded
+    if cfg5_sharded is not None:
+        out["cfg5_refine_sharded"] = cfg5_sharded
     if world == 1:
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(pos, radii, com, tmap, poses, budget_s=args.cpu_budget)
@@ -394,7 +420,7 @@ def run_ours(args):
                              "device_list_equals_host_list_bits": bool(np.array_equal(got_dev, got_host)),
                              "against": "cpu_baseline's CC of the same poses (pose list entries incl. +-1 A shifts)",
                              "cc_gpu_first": float(got_dev[0]), "cc_cpu_first": float(ref_cc[0])}
-        if not args.no_extras:
+        if not args.no_extras and not args.sharded_only:
             out["ops"] = extra_ops(vt, peaks, args)
             if args.cfg4_map > 0:
                 out["cfg4"] = cfg4_legs(vt, peaks, args.cfg4_map)
@@ -627,6 +653,18 @@ def cfg5_leg(vt, natoms, edge):
     res["sim"] = {"atoms": natoms, "map": [sg.xsize, sg.ysize, sg.zsize], "spacing": spacing, "seconds": dt,
                   "voxels_per_s": S.gridsize() / dt, "pairs": pairs, "pairs_per_s": pairs / dt,
                   "note": "vt_sim through the C ABI with host coordinates (sort + upload + splat + min/max)"}
+    refine, ctx = cfg5_refine(vt, pos, radii, mass, quality, radscale, spacing)
+    res["refine"] = refine
+    ctx.close()
+    return res
+
+
+def cfg5_refine(vt, pos, radii, mass, quality, radscale, spacing):
+    """the local rigid refinement of BASELINE configs[4]: two stages of 7^3 Euler triples (4 deg, then 1 deg about the
+    winner) through vt_fit_search_grid.  With the library's communicator up (torchrun, N > 1) every rank calls this on
+    the same inputs and the library shards each stage's candidates (rank r: r, r + N, ...) and merges the per-rank
+    (cc, index) with one ncclAllGather per stage."""
+    from voltool_b200.synth import add_noise
     com = vt.measure_center(pos, mass)
     planted = (8.0, -4.0, 5.0)
     T = vt.sim(vt.pose_apply(pos, com, planted), radii, quality, radscale, spacing)
@@ -634,22 +672,26 @@ def cfg5_leg(vt, natoms, edge):
     ctx = vt.FitContext(pos, radii, T, 3.0)
     lat4 = np.arange(-12.0, 12.1, 4.0)
     lat1 = np.arange(-3.0, 3.1, 1.0)
-    best = np.zeros(3)
-    n_eval = 0
+
+    def two_stages():
+        best, n_eval, best_cc = np.zeros(3), 0, float("nan")
+        for lat in (lat4, lat1):
+            rot = (best[None, :] + np.stack(np.meshgrid(lat, lat, lat, indexing="ij"), -1).reshape(-1, 3)).astype(np.float32)
+            best_cc, idx, pose, _ = ctx.search_grid(com, rot, 0, 0.0)
+            best = rot[idx].astype(np.float64)
+            n_eval += len(rot)
+        return best, n_eval, best_cc
+
+    two_stages()                                           # warm-up: grows the pool by the pose workspaces
     vt.sync()
     t0 = time.perf_counter()
-    for lat in (lat4, lat1):
-        rot = (best[None, :] + np.stack(np.meshgrid(lat, lat, lat, indexing="ij"), -1).reshape(-1, 3)).astype(np.float32)
-        cc = ctx.eval_poses(com, vt.FitContext.make_poses(rot))
-        best = rot[int(np.nanargmax(cc))].astype(np.float64)
-        n_eval += len(rot)
-        best_cc = float(np.nanmax(cc))
+    best, n_eval, best_cc = two_stages()
+    vt.sync()
     dt = time.perf_counter() - t0
-    res["refine"] = {"poses": n_eval, "seconds": dt, "poses_per_s": n_eval / dt, "best_deg": best.tolist(),
-                     "planted_deg": list(planted), "best_cc": best_cc,
-                     "note": "two stages of 7^3 Euler triples (4 deg, then 1 deg about the winner); the planted triple lies on that lattice"}
-    ctx.close()
-    return res
+    return ({"poses": n_eval, "seconds": dt, "poses_per_s": n_eval / dt, "best_deg": best.tolist(),
+             "planted_deg": list(planted), "best_cc": float(best_cc), "batch": ctx.info()["batch"],
+             "note": "two stages of 7^3 Euler triples (4 deg, then 1 deg about the winner) through vt_fit_search_grid; "
+                     "the planted triple lies on that lattice"}, ctx)
 
 
 # ================================================================================================ reference arm
@@ -782,6 +824,8 @@ def main():
     ap.add_argument("--cfg5-edge", type=int, default=400, help="target edge of the cfg5 sim grid")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--sharded-only", action="store_true",
+                    help="keep the all-rank legs (fit_call, cfg5_refine_sharded) but skip rank 0's single-GPU legs and the CPU baseline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3:
