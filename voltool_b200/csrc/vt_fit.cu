@@ -1,4 +1,5 @@
 // vt_fit.cu -- C ABI of sim / calc_cc / fit over the batched pose pipeline (vt_sim.cu).
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -278,10 +279,18 @@ int any_overflow(vt_fit_ctx *f, int *flag) {
 int cuda_table_eval(void *user, const float *origin_pos, const float com[3], int stride, int max_rot, int first,
                     int step, float *table) {
   vt_fit_ctx *f = (vt_fit_ctx *)user;
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = vt_fit_set_origin(f, origin_pos);
   if (rc) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   rc = vt_fit_rotate_table(f, com, stride, max_rot, first, step, table);
   if (rc) return rc;
+  if (getenv("VOLTOOL_VERBOSE")) {
+    const auto t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "voltool_gpu: rotate table stride %d, %d^3 candidates (1 of %d here): set_origin %.2f ms, evaluate %.2f ms\n", stride,
+            max_rot, step, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+            std::chrono::duration<double, std::milli>(t2 - t1).count());
+  }
   // sharded over NCCL: this rank's slice is still in f->d_cc in evaluation order (candidates first, first + step,
   // ...): one allgather of the device slices, and every rank holds the whole table
   if (step > 1 && nccl_active() && !shard_config().merge) rc = nccl_merge_table(f->d_cc, table, max_rot * max_rot * max_rot);
@@ -569,16 +578,28 @@ int vt_fit_rotate_table(vt_fit_ctx *f, const float com[3], int stride, int max_r
 int vt_fit(float *pos, const float *radii, const float *mass, long natoms, const vt_map *target, float resolution,
            vt_fit_result *res) {
   VT_REQUIRE_CTX();
+  const bool verbose = getenv("VOLTOOL_VERBOSE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t0 = now();
   float dencom[3];
   int rc = vt_vol_com(target, dencom);  // :799
   if (rc) return rc;
+  const auto t1 = now();
   // the evaluator context is created on the COM-aligned coordinates inside the schedule: build it
   // on the input coordinates (the atom order/radii are what matter) and let set_origin refresh it
   vt_fit_ctx *f = nullptr;
   rc = vt_fit_create(pos, radii, natoms, target, resolution, &f);
   if (rc) return rc;
+  const auto t2 = now();
   rc = vt_fit_schedule(pos, mass, natoms, dencom, cuda_table_eval, f, res);
+  const auto t3 = now();
   vt_fit_destroy(f);
+  if (verbose)
+    fprintf(stderr, "voltool_gpu: vt_fit: vol_com %.2f ms, workspace %.2f ms, schedule %.2f ms, teardown %.2f ms\n", ms(t0, t1),
+            ms(t1, t2), ms(t2, t3), ms(t3, now()));
   return rc;
 }
 

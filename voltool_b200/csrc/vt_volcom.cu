@@ -7,16 +7,22 @@
 // step is  s <- s + rint(a_i / u) * u  (round to nearest; a tie would consult the parity of s).
 // So for a chunk of addends and a given binade the whole chunk collapses to one integer
 //      T_e = sum_i rint(a_i / u_e)
-// valid whenever (1) no a_i / u_e is an exact half-integer and (2) s cannot leave the binade inside
-// the chunk, which  A_e = sum_i |rint(a_i / u_e)|  bounds.
+// valid whenever s does not leave the binade inside the chunk: the smallest and largest partial sum of the rounded
+// addends (kept per chunk and binade) give the excursion exactly.
+// An exact tie (a_i / u_e = h + 1/2) rounds to the EVEN neighbour of the running sum, so its outcome depends on the
+// parity of the sum when it is reached -- which the parity of the sum at the start of the chunk fixes.  Ties are not
+// rare (an addend within 2^-k of the sum's magnitude ties with probability ~2^-k: signed noise in a map's padding
+// keeps the sum that close to its addends for millions of voxels), so the tables hold the chunk's total for both
+// start parities, T_e[0] and T_e[1], and the walk picks by the parity of s.
 //
 //   pass 1 (parallel, one CTA per chunk): a_i for the three accumulators, and for 26 candidate
-//           binades starting at ceil(log2(sum |a_i|)) the triple (T_e, A_e, tie).  Above that
-//           window the chunk is the identity (|a_i| < u/2), below it the chunk must be replayed.
-//   pass 2 (one warp, lanes 0..2 = x/y/z): walks the chunks in order; a table hit is O(1), anything
-//           else (binade crossing, tie, zero/subnormal sum) replays that chunk add by add.
+//           binades starting at ceil(log2(sum |a_i|)) (T_e[0], T_e[1] - T_e[0], excursions).  Above that
+//           window the chunk is the identity (|a_i| < u/8: kBinades - kBelow = 26 binades up), below it the chunk must be replayed.
+//   pass 2 (one CTA): walks the chunks in order; a table hit is O(1) -- 32 of them at a time by a warp scan -- and
+//           anything else (binade crossing, zero/subnormal sum) replays that chunk add by add.
 // The result equals the sequential loop bit for bit for any input.  The mass is a double sum
 // (order-insensitive to ~1e-16; the reference adds it in voxel order).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -24,11 +30,15 @@
 
 namespace vt {
 
-constexpr int kBinades = 26;
+constexpr int kBinades = 32;   // binades tabulated per chunk and accumulator (one per lane)
+constexpr int kBelow = 6;      // ... of which this many lie below ceil(log2(sum |a_i|)): sums of random sign stay far below sum |a_i|
 
 struct ComEntry {
-  long long T;   // sum of rounded addends, in units of the binade's ulp
-  long long A2;  // (sum of |rounded addends|) << 1 | tie flag
+  long long T0;     // sum of rounded addends in units of the binade's ulp, for an even sum at the start of the chunk
+  int dT;           // ... for an odd one: T0 + dT
+  int lo[2], hi[2]; // smallest / largest partial sum inside the chunk (0 included), per start parity: the exact
+                    // excursion of the running sum (|partial sums| < 2^23 + L inside the window)
+  int pad;
 };
 
 __device__ __forceinline__ float com_addend(const DevCoord &c, int k, float m, int gx, int gy, int gz) {
@@ -65,24 +75,30 @@ __global__ void __launch_bounds__(96) com_tables_kernel(const float *__restrict_
   int e0;
   if (!(tot > 0.0)) e0 = -100000;               // all addends zero: identity in every binade
   else if (!(tot < 1.0e300)) e0 = 100000;       // inf/NaN in the chunk: always replay
-  else { int ex; frexp(tot, &ex); e0 = ex; }    // tot < 2^ex
+  else { int ex; frexp(tot, &ex); e0 = ex - kBelow; }    // tot < 2^ex; the window is [ex - kBelow, ex - kBelow + kBinades)
   if (lane == 0) emin[chunk * 3 + warp] = e0;
   if (lane < kBinades && e0 > -100000 && e0 < 100000) {
     const int e = e0 + lane;
     const double scale = ldexp(1.0, 23 - e);    // 1 / ulp of binade e
-    long long T = 0, A = 0;
-    int tie = 0;
+    long long T0 = 0, T1 = 0, lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
     for (int i = 0; i < cnt; ++i) {
       const double x = (double)a[i] * scale;    // exact
-      const double r = rint(x);
-      tie |= (fabs(x - trunc(x)) == 0.5);
-      const long long ri = (long long)r;
-      T += ri;
-      A += ri < 0 ? -ri : ri;
+      if (fabs(x - trunc(x)) == 0.5) {          // tie: the even one of sum + h, sum + h + 1
+        const long long h = (long long)floor(x);
+        T0 += h + ((T0 + h) & 1);               // parity of the running sum = start parity + total so far
+        T1 += h + ((1 + T1 + h) & 1);
+      } else {
+        const long long ri = (long long)rint(x);
+        T0 += ri; T1 += ri;
+      }
+      lo0 = T0 < lo0 ? T0 : lo0; hi0 = T0 > hi0 ? T0 : hi0;
+      lo1 = T1 < lo1 ? T1 : lo1; hi1 = T1 > hi1 ? T1 : hi1;
     }
     ComEntry en;
-    en.T = T;
-    en.A2 = (A << 1) | tie;
+    en.T0 = T0;
+    en.dT = (int)(T1 - T0);
+    en.lo[0] = (int)lo0; en.hi[0] = (int)hi0; en.lo[1] = (int)lo1; en.hi[1] = (int)hi1;
+    en.pad = 0;
     tab[(chunk * 3 + warp) * kBinades + lane] = en;
   }
 }
@@ -107,7 +123,9 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
   __shared__ long s_chunk;          // chunk to replay / first chunk of the block to prefetch
   __shared__ int s_snap[3];         // exponent bits of each accumulator when the block was prefetched
   __shared__ int s_e0[3][kWalkBlock];
-  __shared__ long long s_T[3][kWalkBlock], s_A2[3][kWalkBlock];
+  __shared__ long long s_T[3][kWalkBlock];
+  __shared__ int s_dT[3][kWalkBlock];
+  __shared__ int s_lo[3][2][kWalkBlock], s_hi[3][2][kWalkBlock];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long nxy = (long)c.nx * c.ny;
 
@@ -130,14 +148,15 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
   auto prefetch = [&](long first) {
     const long chunk = first + tid;
     if (chunk < nchunks) {
-#pragma unroll
-      for (int kk = 0; kk < 3; ++kk) {
+      {
+        const int kk = blockIdx.x;
         const int e0 = emin[chunk * 3 + kk];
         const int j = (s_snap[kk] - 127) - e0;
         ComEntry en;
-        en.T = 0; en.A2 = 0;
+        en.T0 = 0; en.dT = 0; en.lo[0] = en.lo[1] = en.hi[0] = en.hi[1] = 0;
         if (e0 > -100000 && e0 < 100000 && j >= 0 && j < kBinades) en = tab[(chunk * 3 + kk) * kBinades + j];
-        s_e0[kk][tid] = e0; s_T[kk][tid] = en.T; s_A2[kk][tid] = en.A2;
+        s_e0[kk][tid] = e0; s_T[kk][tid] = en.T0; s_dT[kk][tid] = en.dT;
+        s_lo[kk][0][tid] = en.lo[0]; s_lo[kk][1][tid] = en.lo[1]; s_hi[kk][0][tid] = en.hi[0]; s_hi[kk][1][tid] = en.hi[1];
       }
     }
   };
@@ -155,8 +174,11 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
     return;
   }
 
-  const bool owner = lane < 3;
-  const int k = owner ? lane : 0;
+  // one CTA per accumulator (blockIdx.x = 0, 1, 2 for x, y, z): their walks are independent, and a chunk one of
+  // them has to replay does not hold up the other two
+  const int K = blockIdx.x;
+  const bool owner = lane == K;
+  const int k = K;
   float s = 0.0f;
   int nreplay = 0;
   int snap = 0;
@@ -180,33 +202,38 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
       skip = false;
       if (chunk + 32 <= nchunks) {
         int npass = 0;
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
+        {
+          const int kk = K;
           const unsigned int bits = __float_as_uint(__shfl_sync(0xffffffffu, s, kk));
           const int ebits = (int)((bits >> 23) & 0xff);
           const int snap_k = __shfl_sync(0xffffffffu, snap, kk);
           const long long S = (long long)(bits & 0x7fffffu) | 0x800000ll;
           const long long Ss = (bits >> 31) ? -S : S;
           const int e0 = s_e0[kk][t + lane];
-          long long T = 0, A = 0;
+          long long T0 = 0, T1 = 0;              // this chunk's step for an even / odd sum before it
+          bool tabled = false;
           bool ok = ebits != 0 && ebits != 0xff && ebits == snap_k;
           if (e0 != -100000) {
             const int j = (ebits - 127) - e0;
             if (e0 >= 100000 || j < 0) ok = false;
-            else if (j < kBinades) {
-              const long long a2 = s_A2[kk][t + lane];
-              T = s_T[kk][t + lane]; A = a2 >> 1;
-              if (a2 & 1) ok = false;
-            }
+            else if (j < kBinades) { T0 = s_T[kk][t + lane]; T1 = T0 + s_dT[kk][t + lane]; tabled = true; }
           }
-          long long P = T;   // inclusive prefix of T over the group
+          // inclusive scan of the steps as maps (start parity -> total): (F o G)[p] = F[p] + G[(p + F[p]) & 1]
+          long long P0 = T0, P1 = T1;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
-            const long long v = __shfl_up_sync(0xffffffffu, P, o);
-            if (lane >= o) P += v;
+            const long long q0 = __shfl_up_sync(0xffffffffu, P0, o), q1 = __shfl_up_sync(0xffffffffu, P1, o);
+            if (lane >= o) {   // q = the chunks before this lane's span, P = this lane's span
+              const long long n0 = q0 + ((q0 & 1) ? P1 : P0), n1 = q1 + (((1 + q1) & 1) ? P1 : P0);
+              P0 = n0; P1 = n1;
+            }
           }
-          const long long before = Ss + P - T;
-          const long long lo = before - A, hi = before + A;
+          const long long P = (Ss & 1) ? P1 : P0;                                   // total through this chunk
+          long long Pex = __shfl_up_sync(0xffffffffu, P, 1);                        // ... up to the chunk before
+          if (lane == 0) Pex = 0;
+          const long long before = Ss + Pex;
+          const int par = (int)(before & 1);
+          const long long lo = before + (tabled ? s_lo[kk][par][t + lane] : 0), hi = before + (tabled ? s_hi[kk][par][t + lane] : 0);
           const bool inside = Ss > 0 ? (lo >= 0x800001ll && hi <= 0xfffffell) : (hi <= -0x800001ll && lo >= -0xfffffell);
           // (a chunk without addends, e0 == -100000, changes nothing wherever the sum stands)
           const bool pass = __all_sync(0xffffffffu, ok && (inside || e0 == -100000));
@@ -220,7 +247,7 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
             }
           }
         }
-        if (npass == 3) { chunk += 31; continue; }
+        if (npass == 1) { chunk += 31; continue; }
       }
     }
     bool replay = false;
@@ -234,18 +261,20 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
           const int j = (ebits - 127) - e0;                  // |s| in [2^e, 2^(e+1)), e = ebits-127
           const long long S = (long long)(bits & 0x7fffffu) | 0x800000ll;  // |s| / ulp
           const long long Ss = (bits >> 31) ? -S : S;
-          long long T = 0, A = 0;
-          int tie = 0;
+          long long T = 0, xlo = 0, xhi = 0;   // total and excursion of the chunk for this start parity
           bool have = false;
           if (j >= kBinades) { have = true; }                // every addend rounds to zero
           else if (j >= 0) {
-            ComEntry en;
-            if (ebits == snap) { en.T = s_T[k][t]; en.A2 = s_A2[k][t]; }
-            else en = tab[(chunk * 3 + k) * kBinades + j];   // the sum left the prefetched binade inside this block
-            T = en.T; A = en.A2 >> 1; tie = (int)(en.A2 & 1); have = true;
+            const int par = (int)(Ss & 1);
+            if (ebits == snap) { T = s_T[k][t] + (par ? s_dT[k][t] : 0); xlo = s_lo[k][par][t]; xhi = s_hi[k][par][t]; }
+            else {                                           // the sum left the prefetched binade inside this block
+              const ComEntry en = tab[(chunk * 3 + k) * kBinades + j];
+              T = en.T0 + (par ? en.dT : 0); xlo = en.lo[par]; xhi = en.hi[par];
+            }
+            have = true;
           }
-          if (have && !tie) {
-            const long long lo = Ss - A, hi = Ss + A;
+          if (have) {
+            const long long lo = Ss + xlo, hi = Ss + xhi;
             const bool inside =
                 Ss > 0 ? (lo >= 0x800001ll && hi <= 0xfffffell) : (hi <= -0x800001ll && lo >= -0xfffffell);
             if (inside) {
@@ -288,8 +317,8 @@ __global__ void __launch_bounds__(kWalkThreads) com_walk_kernel(const float *__r
   __syncwarp();
   asm volatile("bar.sync 1, %0;" ::"r"(kWalkThreads));
   if (owner) {
-    out[lane] = s;
-    replayed[lane] = nreplay;
+    out[K] = s;
+    replayed[K] = nreplay;
   }
 }
 
@@ -306,8 +335,10 @@ int k_vol_com(const vt_map *m, double out[4]) {
   out[0] = out[1] = out[2] = 0.0;
   out[3] = 0.0;
   if (n <= 0) return 0;
+  // Chunk length: the tables cost 3 x 32 entries of 32 bytes per chunk, a replayed chunk L dependent adds.
   int L = 1024;
-  while (L < 4096 && (n + L - 1) / L > 65536) L *= 2;
+  if (const char *e = getenv("VOLTOOL_COM_CHUNK")) L = std::max(64, std::min(4096, atoi(e) & ~15));
+  while (L < 4096 && (double)((n + L - 1) / L) * 3 * kBinades * sizeof(ComEntry) > 512.0e6) L *= 2;
   const long nchunks = (n + L - 1) / L;
   ComEntry *tab = nullptr;
   int *emin = nullptr;
@@ -326,9 +357,9 @@ int k_vol_com(const vt_map *m, double out[4]) {
   prof_begin(PK_STATS);
   com_tables_kernel<<<(unsigned int)nchunks, 96, smem, c.stream>>>(m->d, n, dc, L, tab, emin);
   VT_LAUNCHED();
-  if (smem > 48 * 1024)
+  if (smem > 16 * 1024)   // (the walk also holds ~27 KB of static shared memory)
     VT_CUDA(cudaFuncSetAttribute(com_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  com_walk_kernel<<<1, kWalkThreads, smem, c.stream>>>(m->d, n, dc, L, nchunks, tab, emin, d_out, (int *)(d_out + 4));
+  com_walk_kernel<<<3, kWalkThreads, smem, c.stream>>>(m->d, n, dc, L, nchunks, tab, emin, d_out, (int *)(d_out + 4));
   prof_end(PK_STATS);
   VT_LAUNCHED();
   float h[8];
