@@ -116,7 +116,7 @@ struct Cfg {
   static constexpr int YQ = (YWIN + 3) / 4;
   static constexpr int Q0 = OFFX / 4, Q1 = (OFFX + 16 + 2 * R - 1) / 4;   // 16-byte chunks of a staged row the x pass reads
   static constexpr int T_BYTES = TXW * PY * 4;
-  static constexpr size_t SMEM = (size_t)S * STAGE_BYTES + (size_t)D * T_BYTES + 16 * (S + D) + 1024;
+  static constexpr size_t SMEM = (size_t)S * STAGE_BYTES + (size_t)D * T_BYTES + 16 * (S + D) + 1024;   // (barriers: 16 bytes per group of 3)
   static_assert(TXW == 16 && TYH % 4 == 0 && R >= 1 && R <= 8 && 3 * ROWS <= NTHR, "tile shape");
   static_assert(BX * 4 == 128, "a staged row is one 128-byte swizzle span");
 };
@@ -208,21 +208,28 @@ __device__ __forceinline__ void mbar_arrive(unsigned int bar) {
 // The x pass of THREE planes is spread over the whole CTA (thread t: row t % ROWS of plane 3g + t / ROWS), one
 // group of three planes ahead of the y / z work, so every thread carries the same load and warps only ever wait
 // for data, not for each other.
+// warps that hold x-role rows of the planes q with q % 3 == k (threads k ROWS .. (k + 1) ROWS - 1)
+template <int ROWS>
+__host__ __device__ constexpr int x_warps(int k) { return ((k + 1) * ROWS - 1) / 32 - (k * ROWS) / 32 + 1; }
+
 template <int R, int TXW, int TYH, bool USE_TMA>
-__global__ void __launch_bounds__(Cfg<R, TXW, TYH>::NTHR, 2)
+__global__ void __launch_bounds__(Cfg<R, TXW, TYH>::NTHR + 32, 2)
     blur_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ src, float *__restrict__ out, int nx, int ny,
                     int nz, int xt, int tiles, int zchunk, int abl) {
   using C = Cfg<R, TXW, TYH>;
   constexpr int NT = C::NT, BX = C::BX, ROWS = C::ROWS, PY = C::PY, S = C::S, D = C::D, NTHR = C::NTHR;
+  static_assert(S % 3 == 0 && D % 3 == 0, "a ring slot always holds planes of one x-role group");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const unsigned int sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;          // shared-window byte addresses throughout
   const unsigned int tbase = sbase + S * C::STAGE_BYTES;
   const unsigned int bars = tbase + D * C::T_BYTES;
+  // every barrier counts WARPS, not threads (an arrive per thread made the handshakes alone cost 0.26 ms at 512^3): the
+  // lanes of a warp that share a plane meet at a __syncwarp and one of them arrives
   const unsigned int raw_full = bars, raw_empty = bars + 8 * S, t_full = bars + 16 * S, t_empty = bars + 16 * S + 8 * D;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(raw_full + 8 * s, 1); mbar_init(raw_empty + 8 * s, ROWS); }
-    for (int s = 0; s < D; ++s) { mbar_init(t_full + 8 * s, ROWS); mbar_init(t_empty + 8 * s, NTHR); }
+    for (int s = 0; s < S; ++s) { mbar_init(raw_full + 8 * s, 1); mbar_init(raw_empty + 8 * s, x_warps<ROWS>(s % 3)); }
+    for (int s = 0; s < D; ++s) { mbar_init(t_full + 8 * s, x_warps<ROWS>(s % 3)); mbar_init(t_empty + 8 * s, NTHR / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -254,21 +261,22 @@ __global__ void __launch_bounds__(Cfg<R, TXW, TYH>::NTHR, 2)
   const size_t nxy = (size_t)nx * ny;
   const unsigned int ywin = tbase + (unsigned int)(lx * PY + 4 * rg) * 4u;   // this thread's y window in T slot 0
 
-  int issued = 0;   // planes handed to TMA (thread 0 only)
-  // A stage is refilled once every thread that x-passed its last plane has arrived.  blocking: up to plane `upto` no
-  // matter what (before thread 0 itself waits for that plane); otherwise as far as the ring is free right now.
-  auto issue_planes = [&](int upto, bool blocking) {
-    upto = min(upto, nplanes - 1);
-    while (USE_TMA && !(abl & 16) && issued <= upto) {
-      const unsigned int st = (unsigned int)issued % S, par = (((unsigned int)issued / S) & 1u) ^ 1u;
-      if (blocking) mbar_wait(raw_empty + 8 * st, par);
-      else if (!mbar_test(raw_empty + 8 * st, par)) break;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(raw_full + 8 * st, (unsigned int)(BX * ROWS * sizeof(float)));
-      tma_load_3d(sbase + st * C::STAGE_BYTES, &tmap, x0 - C::RA, y0 - R, pf + issued, raw_full + 8 * st);
-      ++issued;
+  if (tid >= NTHR) {   // producer warp: one lane keeps the TMA ring full, S planes ahead of the x pass
+    if (USE_TMA && !(abl & 16) && tid == NTHR) {
+      for (int i = 0; i < nplanes; ++i) {
+        const unsigned int st = (unsigned int)i % S, par = (((unsigned int)i / S) & 1u) ^ 1u;
+        mbar_wait(raw_empty + 8 * st, par);             // every warp that x-passed the stage's last plane has arrived
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(raw_full + 8 * st, (unsigned int)(BX * ROWS * sizeof(float)));
+        tma_load_3d(sbase + st * C::STAGE_BYTES, &tmap, x0 - C::RA, y0 - R, pf + i, raw_full + 8 * st);
+      }
     }
-  };
+    return;
+  }
+  // the lanes of this warp that x-pass rows of the same plane, and the one that arrives for them
+  const unsigned int xmask = __match_any_sync(0xffffffffu, xrole ? xq : -1);
+  const bool xlead = xrole && (tid & 31) == __ffs(xmask) - 1;
+  const bool wlead = (tid & 31) == 0;
   // x pass of plane q (this thread's row) into T slot q % D
   auto x_phase = [&](int q) {
     const unsigned int stg = (unsigned int)q % S, slot = (unsigned int)q % D;
@@ -282,7 +290,8 @@ __global__ void __launch_bounds__(Cfg<R, TXW, TYH>::NTHR, 2)
         const float4 f = lds128(ra ^ ((unsigned int)qd << 4));
         in[4 * qd] = f.x; in[4 * qd + 1] = f.y; in[4 * qd + 2] = f.z; in[4 * qd + 3] = f.w;
       }
-      mbar_arrive(raw_empty + 8 * stg);              // the row is in registers: the stage may be refilled
+      __syncwarp(xmask);                             // the rows are in registers: the stage may be refilled
+      if (xlead && !(abl & 16)) mbar_arrive(raw_empty + 8 * stg);
       if (xborder) {                                 // clamp to edge in x, in registers
         if (cx0 > 0) {
 #pragma unroll
@@ -315,7 +324,8 @@ __global__ void __launch_bounds__(Cfg<R, TXW, TYH>::NTHR, 2)
       sts32(ta + (2 * p) * PY * 4, lo);
       sts32(ta + (2 * p + 1) * PY * 4, hi);
     }
-    mbar_arrive(t_full + 8 * slot);
+    __syncwarp(xmask);
+    if (xlead) mbar_arrive(t_full + 8 * slot);
   };
 
   f32x2 acc[2][NT];
@@ -325,7 +335,6 @@ __global__ void __launch_bounds__(Cfg<R, TXW, TYH>::NTHR, 2)
     for (int k = 0; k < NT; ++k) acc[c][k] = pack2(0.0f, 0.0f);
   f32x2 v[2] = {pack2(0.0f, 0.0f), pack2(0.0f, 0.0f)};
 
-  if (tid == 0) issue_planes(S - 1, true);
   if (xrole && xq < nplanes) x_phase(xq);           // group 0
   int s = ((zlo - R) % NT + NT) % NT;
   int p = 0;                                        // next plane to consume
@@ -333,10 +342,6 @@ __global__ void __launch_bounds__(Cfg<R, TXW, TYH>::NTHR, 2)
   for (int zin = zlo - R; zin < zhi + R; ++zin) {
     const int zp = zin < 0 ? 0 : (zin > nz - 1 ? nz - 1 : zin);   // clamp to edge: virtual planes repeat the border plane
     if (zp - pf == p) {                             // a new plane: uniform over the CTA
-      if (tid == 0) {
-        if (p3 == 0) issue_planes(p + 3, true);     // the plane thread 0 is about to x-pass must be on its way
-        issue_planes(p + 3 + S, false);
-      }
       if (p3 == 0 && xrole && p + 3 + xq < nplanes) x_phase(p + 3 + xq);   // the next group of three planes
       const unsigned int slot = (unsigned int)p % D;
       mbar_wait(t_full + 8 * slot, ((unsigned int)p / D) & 1u);
@@ -346,7 +351,8 @@ __global__ void __launch_bounds__(Cfg<R, TXW, TYH>::NTHR, 2)
         const float4 f = lds128(ywin + slot * C::T_BYTES + 16u * qd);
         win[4 * qd] = f.x; win[4 * qd + 1] = f.y; win[4 * qd + 2] = f.z; win[4 * qd + 3] = f.w;
       }
-      mbar_arrive(t_empty + 8 * slot);
+      __syncwarp();
+      if (wlead) mbar_arrive(t_empty + 8 * slot);
       if (abl & 8) { v[0] = pack2(win[0], win[1]); v[1] = pack2(win[2], win[3]); }
       else conv_pairs<R, 4, 0, 4 * C::YQ>(win, v);
       ++p;
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(Cfg<R, TXW, TYH>::NTHR, 2)
     }
     const bool emit = zin - R >= zlo;               // the output completed by this step
     if (abl & 2) {
-      if (emit && !(abl & 1)) { float a_, b_; unpack2(v[0], a_, b_); __stcs(o, a_); __stcs(o + nx, b_); unpack2(v[1], a_, b_); __stcs(o + 2 * nx, a_); __stcs(o + 3 * nx, b_); }
+      if (emit && !(abl & 1) && okmask == 15u) { float a_, b_; unpack2(v[0], a_, b_); __stcs(o, a_); __stcs(o + nx, b_); unpack2(v[1], a_, b_); __stcs(o + 2 * nx, a_); __stcs(o + 3 * nx, b_); }
     } else z_dispatch<R>(s, acc, v, emit && !(abl & 1), o, nx, okmask);
     if (emit) o += nxy;
     s = s + 1 == NT ? 0 : s + 1;
@@ -375,7 +381,7 @@ static int launch(const float *src, float *dst, int nx, int ny, int nz) {
   if (!ctas_per_sm) {
     VT_CUDA(cudaFuncSetAttribute(blur_tma_kernel<R, TXW, TYH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     VT_CUDA(cudaFuncSetAttribute(blur_tma_kernel<R, TXW, TYH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, C::NTHR, C::SMEM));
+    VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, C::NTHR + 32, C::SMEM));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
   // z chunks: one CTA per (tile, chunk).  More chunks fill the machine when there are few tiles, and even out the
@@ -396,7 +402,7 @@ static int launch(const float *src, float *dst, int nx, int ny, int nz) {
   const int zchunk = (nz + best_zc - 1) / best_zc;
   const long items = tiles * ((nz + zchunk - 1) / zchunk);
   if (items > 0x7fffffffL) return 1;
-  kern<<<(unsigned int)items, C::NTHR, C::SMEM, c.stream>>>(map, src, dst, nx, ny, nz, xt, (int)tiles, zchunk,
+  kern<<<(unsigned int)items, C::NTHR + 32, C::SMEM, c.stream>>>(map, src, dst, nx, ny, nz, xt, (int)tiles, zchunk,
                                                             getenv("VOLTOOL_BLUR_ABL") ? atoi(getenv("VOLTOOL_BLUR_ABL")) : 0);
   VT_LAUNCHED();
   return 0;
