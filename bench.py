@@ -148,6 +148,20 @@ def splat_pairs(radii, radscale, gspacing, gausslim=4.0):
     return float(np.sum(b ** 3))
 
 
+def splat_traffic(args, poses_per_launch):
+    """dram__bytes_read + dram__bytes_write of one splat_list_kernel launch, as MEASURED by the committed ncu --set full
+    capture of this build (profiles/r2l_splat_traffic.json is written from the capture's summary); only quoted for the
+    configuration that capture ran (cfg2, same poses per launch), else null"""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2l_splat_traffic.json")
+    try:
+        t = json.load(open(path))
+    except Exception:
+        return None, "no ncu capture of this build under profiles/"
+    if args.atoms != 50000 or args.map != 256 or abs(poses_per_launch - t["poses_per_launch"]) > 0.5:
+        return None, f"{t['source']} is of cfg2 at {t['poses_per_launch']} poses per launch, not this configuration"
+    return t["traffic"], t["source"]
+
+
 def build_cfg2(vt, atoms, n):
     """BASELINE configs[1] on the device: `atoms` atoms in a ball, target = 1 A density of the structure in the
     PLANTED pose, zero-padded to n^3, + N(0, 0.02 max) noise; the structure is then COM-aligned to the map as
@@ -373,12 +387,12 @@ def run_ours(args):
     achieved = FLOP_PER_PAIR * pairs * poses_done / (splat_ms * 1e-3) / 1e12 if splat_ms > 0 else None
     roofline = {"kernel": "splat_list_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": (achieved / fp32_peak) if achieved else None,
-                "traffic": 5.15e8 * (splat_n and (P * K / splat_n) / 128.0) if args.atoms == 50000 else None,
-                "traffic_source": "profiles/r1k_splat_list_kernel_summary.txt: dram read 285 MB + write 230 MB per 128 poses",
+                "traffic": splat_traffic(args, P * K / max(splat_n, 1))[0],
+                "traffic_source": splat_traffic(args, P * K / max(splat_n, 1))[1],
                 "peak_source": f"{props['sm_count']} SMs x 128 lanes x 2 x sm_max_mhz ({peaks['source']} MEASURED_PEAKS); "
                                "no tensor cores: nothing here is a contraction",
-                "binding_resource": "shared-memory pipe, then instruction issue (ncu of this kernel alone: l1tex 71 % busy, "
-                                    "issue 71 %; profiles/r1k_splat_list_kernel_summary.txt); only ~1 in 7 (atom, voxel) "
+                "binding_resource": "shared-memory pipe, then instruction issue (ncu of this kernel inside the fit step: l1tex 74 % "
+                                    "busy, issue 72 %; profiles/r2l_splat_list_kernel_summary.txt); only ~1 in 7 (atom, voxel) "
                                     "evaluations of a warp lands inside the atom's cutoff box, which is what `frac` shows",
                 "pairs_per_pose": pairs, "flop_per_pair": FLOP_PER_PAIR,
                 "ms_per_launch": splat_ms / max(splat_n, 1), "launches": splat_n,
@@ -474,7 +488,17 @@ def extra_ops(vt, peaks, args):
     gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
     res["correlate_offset"] = {"map": [n, n, n], "ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"],
                                "bytes_per_voxel": 8, "cc": vt.cc_threaded(A, B_off),
-                               "path": "B origin +0.5 voxel in x: shared-memory ring, trilinear"}
+                               "path": "B origin +0.5 voxel in x: real trilinear interpolation; regular sampling -> cc_lean_kernel "
+                                       "(packed column pairs, tensor-map TMA ring)"}
+    # both maps on ONE lattice whose spacing is not exactly representable (1.06 A): the float index arithmetic jitters,
+    # some steps repeat or skip a source plane -> the general ring kernel
+    g_j = vt.Grid.make((0, 0, 0), (n, n, n), 1.06)
+    A_j, B_j = vt.VolMap(g_j, a), vt.VolMap(g_j, b)
+    ms = timeit("cc", lambda: vt.cc_threaded(A_j, B_j))
+    gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
+    res["correlate_jitter"] = {"map": [n, n, n], "ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8,
+                               "cc": vt.cc_threaded(A_j, B_j), "path": "spacing 1.06 A on both maps: irregular index steps, general ring kernel"}
+    del A_j, B_j
     ms = timeit("binary", lambda: vt.add(A, B))
     gbs = 12.0 * g.n / (ms * 1e-3) / 1e9
     res["add"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 12,
@@ -482,7 +506,7 @@ def extra_ops(vt, peaks, args):
     ms = timeit("binary", lambda: vt.add(A, B_off))
     gbs = 12.0 * g.n / (ms * 1e-3) / 1e9
     res["add_offset"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 12,
-                         "path": "B origin +0.5 voxel in x: shared-memory ring, trilinear"}
+                         "path": "B origin +0.5 voxel in x: cc_lean_kernel (packed column pairs, tensor-map TMA ring)"}
     del B_off
     ms = timeit("unary", lambda: A.scalar_add(0.0))
     gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
@@ -500,7 +524,11 @@ def extra_ops(vt, peaks, args):
     ms = timeit("blur", lambda: C.gaussian_blur(2.0), reps=3)
     gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
     res["smooth_sigma2"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8,
-                            "note": "x+y fused per plane tile, then z: two passes move 16 B/voxel"}
+                            "note": "13 taps: x+y fused per plane tile, then z: two passes move 16 B/voxel"}
+    ms = timeit("blur", lambda: C.gaussian_blur(1.0), reps=3)
+    gbs = 8.0 * g.n / (ms * 1e-3) / 1e9
+    res["smooth_sigma1"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / peaks["hbm_gbs"], "bytes_per_voxel": 8,
+                            "note": "7 taps: ONE pass over HBM, tensor-map TMA staging (blur_tma_kernel)"}
     def resample_leg(op):
         vt.profile_reset(); vt.profile_enable(True)
         reps = 3
@@ -620,7 +648,7 @@ def cfg4_legs(vt, peaks, n):
     leg("correlate", "cc", lambda: vt.cc_threaded(A, B), 8, cc=vt.cc_threaded(A, B), analytic_cc=0.919145,
         path="one exact lattice: streamed")
     leg("correlate_offset", "cc", lambda: vt.cc_threaded(A, B_off), 8, cc=vt.cc_threaded(A, B_off),
-        path="B origin +0.5 voxel in x: shared-memory ring, trilinear")
+        path="B origin +0.5 voxel in x: real trilinear interpolation, cc_lean_kernel (packed column pairs, tensor-map TMA ring)")
     leg("add", "binary", lambda: vt.add(A, B), 12)
     leg("diff", "binary", lambda: vt.subtract(A, B), 12)
     leg("add_offset", "binary", lambda: vt.add(A, B_off), 12)
