@@ -349,6 +349,38 @@ def run_ours(args):
                                      if world > 1 else "none (one rank)",
                        "note": "whole vt_fit call incl. vol_com of the 256^3 target and the workspace set-up; max over ranks, best of 3"}
 
+    # ---- the same cfg2 search as ONE call of the search API (vt_fit_search_grid): rotations x 27 translations, the
+    # translated candidates of a rotation share that rotation's splat (the density of a translated structure is the same
+    # voxels on a translated frame), ranks split the rotations, one ncclAllGather of (cc, index).  Reported beside the
+    # headline, not as it: the headline scores an arbitrary pose list one splat per pose.
+    grid_search = None
+    if not args.no_extras:
+        rx, ry, rz = np.arange(25) * (360.0 / 25), np.arange(20) * (360.0 / 20), np.arange(20) * (360.0 / 20)
+        rots = np.stack(np.meshgrid(rx, ry, rz, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+        rots = np.ascontiguousarray(rots[np.random.default_rng(2004).permutation(len(rots))[:args.grid_rotations * world]])
+        ctx.search_grid(com, rots[:64], 1, 1.0)             # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        gcc, gidx, gpose, _ = ctx.search_grid(com, rots, 1, 1.0)
+        vt.sync()
+        dt = time.perf_counter() - t0
+        # a sample of the same candidates scored the per-pose way (own transform + splat each)
+        os.environ["VOLTOOL_GRID_SHARED"] = "0"
+        _, _, _, ref_all = ctx.search_grid(com, rots[:8], 1, 1.0, want_all=True) if world == 1 else (0, 0, 0, None)
+        os.environ.pop("VOLTOOL_GRID_SHARED")
+        sh_all = ctx.search_grid(com, rots[:8], 1, 1.0, want_all=True)[3] if world == 1 else None
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ncand = len(rots) * 27
+        grid_search = {"rotations": len(rots), "translations": 27, "candidates": ncand, "seconds": float(tt[0].item()),
+                       "poses_per_s": ncand / float(tt[0].item()), "ranks": world, "best_cc": float(gcc), "best_index": int(gidx),
+                       "best_pose": [float(v) for v in gpose],
+                       "max_rel_diff_vs_per_pose_path": (float(np.nanmax(np.abs(sh_all - ref_all) / np.maximum(np.abs(ref_all), 1e-3)))
+                                                         if sh_all is not None else None),
+                       "note": "vt_fit_search_grid with host rotation list in, winner out; one splat per rotation, 27 re-aimed cc "
+                               "passes (batch_retarget); tol 1e-5 on CC against the per-pose path (tests/test_gpu_extras.py)"}
+
     # ---- cfg5's "fit with local rigid refinement on N GPUs": every rank holds the 250k-atom structure and the ~400^3
     # target; each refinement stage is sharded by the library and merged with one ncclAllGather of (cc, index)
     cfg5_sharded = None
@@ -416,6 +448,8 @@ def run_ours(args):
         out["fit_call"] = fit_sharded
     if cfg5_sharded is not None:
         out["cfg5_refine_sharded"] = cfg5_sharded
+    if grid_search is not None:
+        out["grid_search"] = grid_search
     if world == 1:
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(pos, radii, com, tmap, poses, budget_s=args.cpu_budget)
@@ -851,6 +885,7 @@ def main():
     ap.add_argument("--cfg5-atoms", type=int, default=250000, help="atoms of the cfg5 leg (0: skip)")
     ap.add_argument("--cfg5-edge", type=int, default=400, help="target edge of the cfg5 sim grid")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--grid-rotations", type=int, default=1024, help="rotations per GPU of the grid_search leg (x 27 translations)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--sharded-only", action="store_true",
                     help="keep the all-rank legs (fit_call, cfg5_refine_sharded) but skip rank 0's single-GPU legs and the CPU baseline")

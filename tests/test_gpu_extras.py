@@ -182,3 +182,27 @@ def test_search_grid_equals_oracle(oracle):
     # the planted pose wins: rotation (24, 0, 48), shift (+1, 0, -1)
     assert ir == 1 and tuple(bpose[3:]) == (1.0, 0.0, -1.0)
     ctx.close()
+
+
+def test_search_grid_shared_splat_equals_per_pose_path(oracle, monkeypatch):
+    """translated candidates of one rotation share that rotation's splat (batch_retarget): every score must agree with
+    the path that transforms and splats each candidate separately (1e-5 on CC; measured ~1e-7), same winner"""
+    pos, radii, mass = make_structure(3000, 18.0, seed=83)
+    gT, t = make_target(oracle, pos, radii, 5.0, 1.0, rot=(48, 24, 0), noise=0.02, seed=84, mass=mass)
+    gT.origin[1] += 1.5
+    target = vt.VolMap(G(gT), t)
+    com = vt.measure_center(pos, mass)
+    r = np.random.default_rng(85)
+    rots = np.concatenate([np.array([[48, 24, 0], [0, 0, 0]], np.float32), (r.random((300, 3)) * 360).astype(np.float32)])
+    ctx = vt.FitContext(pos, radii, target, 5.0)
+    monkeypatch.setenv("VOLTOOL_GRID_SHARED", "0")
+    c0, i0, p0, all0 = ctx.search_grid(com, rots, 1, 1.5, want_all=True)
+    monkeypatch.delenv("VOLTOOL_GRID_SHARED")
+    c1, i1, p1, all1 = ctx.search_grid(com, rots, 1, 1.5, want_all=True)
+    ok = ~np.isnan(all0)
+    assert np.array_equal(np.isnan(all1), np.isnan(all0)) and ok.sum() > 8000
+    rel = np.abs(all1[ok] - all0[ok]) / np.maximum(np.abs(all0[ok]), 1e-3)
+    assert rel.max() < 1e-5, rel.max()
+    assert i1 == i0 and np.array_equal(p1, p0) and abs(c1 - c0) <= 1e-5 * abs(c0)
+    assert i1 // 27 == 0 and tuple(p1[3:]) == (0.0, 1.5, 0.0)              # the planted rotation and shift
+    ctx.close()

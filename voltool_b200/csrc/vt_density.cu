@@ -42,6 +42,42 @@ int density_pose(vt_map *S, const float com[3], int stride, const int amt[3]) {
   return 0;
 }
 
+// merge of the per-rank winners (one ncclAllGather of (cc, index bits) per rank; every rank then picks the same one)
+template <class PoseOf>
+int finish_search(const ShardConfig &sh, bool sharded, float bv, long bi, float *best_cc, long *best_index, vt_pose *best_pose,
+                  PoseOf pose_of) {
+  if (sharded) {
+    Ctx &c = ctx();
+    float *d_buf = nullptr;
+    if (dev_alloc((void **)&d_buf, sizeof(float) * 2 * (size_t)(sh.world + 1))) return 2;
+    float mine[2];
+    const int bi32 = (int)bi;
+    mine[0] = bv;
+    memcpy(&mine[1], &bi32, sizeof(int));
+    std::vector<float> all(2 * (size_t)sh.world);
+    int rc = 0;
+    cudaError_t e = cudaMemcpyAsync(d_buf, mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);   // `mine` is pageable
+    if (e == cudaSuccess) rc = vt_nccl_allgather(d_buf, d_buf + 2, 2);
+    if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(all.data(), d_buf + 2, sizeof(float) * all.size(), cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(c.stream);
+    dev_free(d_buf);
+    if (e != cudaSuccess) return cuda_fail(e, "vt_fit_search_grid merge", __FILE__, __LINE__);
+    if (rc) return rc;
+    bv = -INFINITY; bi = -1;
+    for (int r = 0; r < sh.world; ++r) {
+      int idx;
+      memcpy(&idx, &all[2 * r + 1], sizeof(int));
+      const float v = all[2 * r];
+      if (idx >= 0 && (v > bv || (v == bv && idx < bi))) { bv = v; bi = idx; }
+    }
+  }
+  *best_cc = bi >= 0 ? bv : NAN;
+  *best_index = bi;
+  if (best_pose && bi >= 0) *best_pose = pose_of(bi);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -107,6 +143,35 @@ int vt_fit_search_grid(vt_fit_ctx *fctx, const float com[3], const float *rot_de
     p.shift[2] = (float)(iz - tsteps) * tstep;
     return p;
   };
+  // translations of one rotation share that rotation's splat (fit_eval_rot_shifts): ranks then split the ROTATIONS
+  const char *shared_env = getenv("VOLTOOL_GRID_SHARED");
+  if (tsteps > 0 && !(shared_env && atoi(shared_env) == 0)) {
+    std::vector<float> shifts(3 * (size_t)per_rot);
+    for (long it = 0; it < per_rot; ++it) {
+      const vt_pose q = pose_of(it);
+      for (int k = 0; k < 3; ++k) shifts[3 * it + k] = q.shift[k];
+    }
+    std::vector<float> rots;
+    std::vector<long> rot_index;
+    for (long ir = first; ir < nrot; ir += step) {
+      rot_index.push_back(ir);
+      for (int k = 0; k < 3; ++k) rots.push_back(rot_deg[3 * ir + k]);
+    }
+    std::vector<float> cc(rot_index.size() * (size_t)per_rot + 1);
+    int rc = fit_eval_rot_shifts(fctx, com, rots.data(), (long)rot_index.size(), shifts.data(), (int)per_rot, cc.data());
+    if (rc) return rc;
+    if (cc_all && sharded) for (long i = 0; i < total; ++i) cc_all[i] = NAN;
+    float bv = -INFINITY;
+    long bi = -1;
+    for (size_t r = 0; r < rot_index.size(); ++r)   // ascending candidate index: `if (cc > best)` keeps the first maximum
+      for (long it = 0; it < per_rot; ++it) {
+        const float v = cc[r * per_rot + it];
+        const long idx = rot_index[r] * per_rot + it;
+        if (cc_all) cc_all[idx] = v;
+        if (v > bv) { bv = v; bi = idx; }
+      }
+    return finish_search(sh, sharded, bv, bi, best_cc, best_index, best_pose, pose_of);
+  }
   std::vector<vt_pose> poses;
   poses.reserve((size_t)((total - first + step - 1) / step));
   for (long idx = first; idx < total; idx += step) poses.push_back(pose_of(idx));
@@ -122,35 +187,7 @@ int vt_fit_search_grid(vt_fit_ctx *fctx, const float com[3], const float *rot_de
     if (sharded) for (long i = 0; i < total; ++i) cc_all[i] = NAN;   // a rank only knows its own candidates
     for (size_t k = 0; k < poses.size(); ++k) cc_all[first + (long)k * step] = cc[k];
   }
-  if (sharded) {   // one allgather of (cc, index bits) per rank; every rank then picks the same winner
-    Ctx &c = ctx();
-    float *d_buf = nullptr;
-    if (dev_alloc((void **)&d_buf, sizeof(float) * 2 * (size_t)(sh.world + 1))) return 2;
-    float mine[2];
-    const int bi32 = (int)bi;
-    mine[0] = bv;
-    memcpy(&mine[1], &bi32, sizeof(int));
-    std::vector<float> all(2 * (size_t)sh.world);
-    cudaError_t e = cudaMemcpyAsync(d_buf, mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);   // `mine` is pageable
-    if (e == cudaSuccess) rc = vt_nccl_allgather(d_buf, d_buf + 2, 2);
-    if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(all.data(), d_buf + 2, sizeof(float) * all.size(), cudaMemcpyDeviceToHost, c.stream);
-    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(c.stream);
-    dev_free(d_buf);
-    if (e != cudaSuccess) return cuda_fail(e, "vt_fit_search_grid merge", __FILE__, __LINE__);
-    if (rc) return rc;
-    bv = -INFINITY; bi = -1;
-    for (int r = 0; r < sh.world; ++r) {
-      int idx;
-      memcpy(&idx, &all[2 * r + 1], sizeof(int));
-      const float v = all[2 * r];
-      if (idx >= 0 && (v > bv || (v == bv && idx < bi))) { bv = v; bi = idx; }
-    }
-  }
-  *best_cc = bi >= 0 ? bv : NAN;
-  *best_index = bi;
-  if (best_pose && bi >= 0) *best_pose = pose_of(bi);
-  return 0;
+  return finish_search(sh, sharded, bv, bi, best_cc, best_index, best_pose, pose_of);
 }
 
 }  // extern "C"

@@ -306,5 +306,10 @@ int k_supersample(const float *src, int ox, int oy, int oz, float *dst);
 int k_blur(const float *src, float *dst, float *tmp, int nx, int ny, int nz, const float *w, int R);
 int k_vol_com(const vt_map *m, double out[4]);
 int k_histogram(const float *d, long n, float mn, double binwidthinv, int nbins, unsigned long long *d_bins);
+}  // namespace vt
+struct vt_fit_ctx;
+namespace vt {
+// rotations x shifts with one splat per rotation (vt_fit.cu); cc_out[ir * ns + s] on the host
+int fit_eval_rot_shifts(vt_fit_ctx *f, const float com[3], const float *rot_deg, long nrot, const float *shifts, int ns, float *cc_out);
 
 }  // namespace vt

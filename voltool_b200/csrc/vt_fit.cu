@@ -55,8 +55,11 @@ int sim_to_map(const float *pos, const float *radii, long natoms, int quality, f
   VT_REQUIRE_CTX();
   if (!pos || !radii || natoms <= 0 || !(gspacing > 0.f)) { set_error("vt_sim: bad arguments"); return 1; }
   AtomSet as;
+  const bool verbose = getenv("VOLTOOL_VERBOSE") != nullptr;
+  const auto ts0 = std::chrono::steady_clock::now();
   int rc = atomset_create(pos, radii, natoms, make_params(quality, radscale, gspacing), as);
   if (rc) return rc;
+  const auto ts1 = std::chrono::steady_clock::now();
   // exact grid size on the host (same float expressions as pose_setup_kernel) to size the slot
   float mn[3] = {pos[0], pos[1], pos[2]}, mx[3] = {pos[0], pos[1], pos[2]};
   for (long i = 0; i < natoms; ++i)
@@ -102,7 +105,12 @@ int sim_to_map(const float *pos, const float *radii, long natoms, int quality, f
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "sim readback", __FILE__, __LINE__);
   };
+  const auto ts2 = std::chrono::steady_clock::now();
   if (!rc) rc = readback();
+  if (verbose)
+    fprintf(stderr, "voltool_gpu: sim_to_map: atom set %.3f ms, allocate + enqueue %.3f ms, wait %.3f ms\n",
+            std::chrono::duration<double, std::milli>(ts1 - ts0).count(), std::chrono::duration<double, std::milli>(ts2 - ts1).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts2).count());
   if (!rc && pb.use_lists && totals[2]) {   // a tile list did not fit: redo with the cooperative kernel
     pb.use_lists = false;
     rc = batch_splat(as, pb, 1);
@@ -257,6 +265,11 @@ int eval_prepared(vt_fit_ctx *f, const float com[3], const PrepPose *d_prep, lon
   return rc;
 }
 
+__global__ void scatter_cc_kernel(const float *__restrict__ src, int n, float *__restrict__ dst, long first, int stride, int offset) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) dst[(first + j) * stride + offset] = src[j];
+}
+
 int reset_overflow(vt_fit_ctx *f) {
   for (int k = 0; k < f->nslots; ++k)
     if (f->pb[k].use_lists) VT_CUDA(cudaMemsetAsync(f->pb[k].d_totals + 2, 0, sizeof(int), ctx().stream));
@@ -299,6 +312,56 @@ int cuda_table_eval(void *user, const float *origin_pos, const float com[3], int
 
 }  // namespace
 
+// Rotation x translation candidates with ONE splat per rotation (vt_fit_search_grid): every rotation of the list is
+// transformed and splatted once, and its grid is then re-aimed at each of the ns translated frames and scored
+// (batch_retarget + the batched cc kernel).  cc_out[ir * ns + s], host.  The translated candidates differ from a
+// separately splatted pose only by the rounding of `origin + shift` against `coordinates + shift` (an ulp of the
+// coordinates): CC agrees to ~1e-7, tested against the per-pose path and against the oracle.
+int vt::fit_eval_rot_shifts(vt_fit_ctx *f, const float com[3], const float *rot_deg, long nrot, const float *shifts, int ns,
+                            float *cc_out) {
+  VT_REQUIRE_CTX();
+  if (nrot <= 0 || ns <= 0) return 0;
+  Ctx &c = ctx();
+  int rc = ensure_cc_buffer(f, nrot * ns + f->B);
+  if (!rc) rc = ensure_prep_buffers(f, nrot, true);
+  if (rc) return rc;
+  VT_CUDA(cudaStreamSynchronize(c.stream));
+  for (long i = 0; i < nrot; ++i)
+    for (int k = 0; k < 3; ++k) {
+      euler_cs((double)rot_deg[3 * i + k], f->h_prep[i].c[k], f->h_prep[i].s[k]);
+      f->h_prep[i].shift[k] = 0.f;
+    }
+  VT_CUDA(cudaMemcpyAsync(f->d_prep, f->h_prep, sizeof(PrepPose) * (size_t)nrot, cudaMemcpyHostToDevice, c.stream));
+  float *d_tmp = f->d_cc + nrot * ns;   // one batch of scores before they are scattered to [rotation][shift]
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    rc = reset_overflow(f);
+    if (rc) return rc;
+    PoseBatch &pb = f->pb[0];
+    for (long i0 = 0; i0 < nrot && !rc; i0 += f->B) {
+      const int n = (int)std::min<long>(f->B, nrot - i0);
+      rc = batch_front(f, pb, com, f->d_prep + i0, n);
+      if (!rc) rc = batch_splat_back(f->as, pb, n);
+      for (int s = 0; s < ns && !rc; ++s) {
+        rc = batch_retarget(f->as, pb, n, shifts + 3 * s, s == 0, &f->target->grid);
+        if (!rc) rc = batch_cc(pb, n, f->target, f->threshold, d_tmp, nullptr);
+        if (!rc) {
+          scatter_cc_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(d_tmp, n, f->d_cc, i0, ns, s);
+          VT_LAUNCHED();
+        }
+      }
+    }
+    if (rc) return rc;
+    VT_CUDA(cudaMemcpyAsync(cc_out, f->d_cc, sizeof(float) * (size_t)(nrot * ns), cudaMemcpyDeviceToHost, c.stream));
+    VT_CUDA(cudaStreamSynchronize(c.stream));
+    int ovf = 0;
+    rc = any_overflow(f, &ovf);
+    if (rc) return rc;
+    if (!ovf) return 0;
+    for (int k = 0; k < 2; ++k) f->pb[k].use_lists = false;   // a tile list was too small: redo with the cooperative kernel
+  }
+  return 0;
+}
+
 extern "C" {
 
 int vt_sim(const float *pos, const float *radii, long natoms, int quality, float radscale, float gspacing,
@@ -336,9 +399,14 @@ int vt_sim_cc(const float *pos, const float *radii, long natoms, double resoluti
   int quality;
   sim_policy(resolution, gspacing_in, radscale, gspacing, quality);
   vt_map *sim = nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = sim_to_map(pos, radii, natoms, quality, radscale, (float)gspacing, synth_out != nullptr, &sim);
   if (rc) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   rc = vt_cc(sim, target, threshold, cc, nullptr, nullptr);
+  if (getenv("VOLTOOL_VERBOSE"))
+    fprintf(stderr, "voltool_gpu: vt_sim_cc: sim %.3f ms, cc %.3f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   if (synth_out && !rc) *synth_out = sim;
   else vt_map_destroy(sim);
   return rc;

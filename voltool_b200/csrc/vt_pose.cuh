@@ -85,6 +85,7 @@ struct PoseBatch {
   geom::AxisEntry *d_tab = nullptr;  // [B][6][cap_o]
   double *d_part = nullptr;          // [B][cap_items][6]
   PrepPose *d_prep = nullptr;        // [B]
+  float *d_org0 = nullptr;           // [B][3]: sim grid origins as splatted (batch_retarget)
 };
 
 int atomset_create(const float *pos, const float *radii, long n, const SimParams &prm, AtomSet &as);
@@ -97,6 +98,9 @@ void batch_destroy(PoseBatch &pb);
 // stage 1: transform (or copy, identity != 0) + bbox + per-pose sim geometry (+ cc geometry if target)
 int batch_prepare(const AtomSet &as, PoseBatch &pb, int npose, const PrepPose *d_prep, const float com[3],
                   int identity, const vt_grid *target);
+// re-aim the batch's splatted grids at the frame translated by `shift` (relative to where they were splatted): new
+// origin, intersection with the target, tables.  first: remember the splatted origins.  Then batch_cc as usual.
+int batch_retarget(const AtomSet &as, PoseBatch &pb, int npose, const float shift[3], bool first, const vt_grid *target);
 // stage 2: splat every pose's density grid
 int batch_splat(const AtomSet &as, PoseBatch &pb, int npose);
 // size and switch on the list-based splat from the pose(s) currently prepared in pb (needs

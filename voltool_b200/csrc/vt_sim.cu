@@ -239,7 +239,7 @@ int batch_create(const AtomSet &as, const vt_grid *target, int B, PoseBatch &pb)
 void batch_destroy(PoseBatch &pb) {
   dev_free(pb.d_tpos); dev_free(pb.d_tgroup); dev_free(pb.d_bbox); dev_free(pb.d_geom); dev_free(pb.d_totals); dev_free(pb.d_bitmap);
   dev_free(pb.d_boxes); dev_free(pb.d_gbox); dev_free(pb.d_tlist); dev_free(pb.d_tcount);
-  dev_free(pb.d_grid); dev_free(pb.d_prep); dev_free(pb.d_tab); dev_free(pb.d_part);
+  dev_free(pb.d_grid); dev_free(pb.d_prep); dev_free(pb.d_tab); dev_free(pb.d_part); dev_free(pb.d_org0);
   pb = PoseBatch();
 }
 
@@ -314,6 +314,34 @@ struct TargetGeom {
   int present;
 };
 
+// the cc half of a pose's geometry: init_from_intersection(sim grid, target) (MDFF.C:132), its cell axes, the sim
+// map's inverse, the work items of the batched cc kernel
+__device__ __forceinline__ void setup_target(PoseGeom &G, const vt_grid &sg, bool ok, const TargetGeom &T, int cap_o) {
+  G.valid = 0;
+  G.cc_items = 0; G.cc_xt = 0; G.cc_zc = 0;
+  for (int k = 0; k < 3; ++k) { G.no[k] = 0; G.oorg[k] = 0; G.od[k] = 0; G.sinv_d[k] = 0; G.sinv_t[k] = 0; }
+  if (ok && T.present) {
+    vt_grid og;
+    geom::intersection_grid(sg, T.grid, og);  // MDFF.C:132 (A = sim, B = target)
+    float xd[3], yd[3], zd[3], sinv[16];
+    geom::cell_axes(og, xd, yd, zd);
+    geom::grid_inverse(sg, false, sinv);
+    const bool aligned = xd[1] == 0.f && xd[2] == 0.f && yd[0] == 0.f && yd[2] == 0.f && zd[0] == 0.f && zd[1] == 0.f;
+    const bool sep = aligned && geom::diagonal_inverse(sinv) && geom::diagonal_inverse(T.inv);
+    G.no[0] = og.xsize; G.no[1] = og.ysize; G.no[2] = og.zsize;
+    const bool fits = og.xsize > 0 && og.ysize > 0 && og.zsize > 0 && og.xsize <= cap_o && og.ysize <= cap_o &&
+                      og.zsize <= cap_o;
+    if (sep && fits) {
+      G.valid = 1;
+      for (int k = 0; k < 3; ++k) { G.oorg[k] = og.origin[k]; G.sinv_d[k] = sinv[5 * k]; G.sinv_t[k] = sinv[12 + k]; }
+      G.od[0] = xd[0]; G.od[1] = yd[1]; G.od[2] = zd[2];
+      G.cc_xt = (og.xsize + 31) / 32;
+      G.cc_zc = (og.zsize + kZChunkFit - 1) / kZChunkFit;
+      G.cc_items = G.cc_xt * ((og.ysize + kRowsFit - 1) / kRowsFit) * G.cc_zc;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) pose_setup_kernel(const unsigned int *__restrict__ bbox, int npose, float pad, float gs, int cap_n,
                                   int cap_o, TargetGeom T, PoseGeom *__restrict__ out, int *__restrict__ totals) {
   for (int p = threadIdx.x; p < npose; p += blockDim.x) {
@@ -342,29 +370,7 @@ __global__ void __launch_bounds__(256) pose_setup_kernel(const unsigned int *__r
     G.tiles[1] = (G.nv[1] + kTY - 1) / kTY;
     G.tiles[2] = (G.nv[2] + kTZ - 1) / kTZ;
     if (!ok) { G.tiles[0] = G.tiles[1] = G.tiles[2] = 0; }
-    G.valid = 0;
-    G.cc_items = 0; G.cc_xt = 0; G.cc_zc = 0;
-    for (int k = 0; k < 3; ++k) { G.no[k] = 0; G.oorg[k] = 0; G.od[k] = 0; G.sinv_d[k] = 0; G.sinv_t[k] = 0; }
-    if (ok && T.present) {
-      vt_grid og;
-      geom::intersection_grid(sg, T.grid, og);  // MDFF.C:132 (A = sim, B = target)
-      float xd[3], yd[3], zd[3], sinv[16];
-      geom::cell_axes(og, xd, yd, zd);
-      geom::grid_inverse(sg, false, sinv);
-      const bool aligned = xd[1] == 0.f && xd[2] == 0.f && yd[0] == 0.f && yd[2] == 0.f && zd[0] == 0.f && zd[1] == 0.f;
-      const bool sep = aligned && geom::diagonal_inverse(sinv) && geom::diagonal_inverse(T.inv);
-      G.no[0] = og.xsize; G.no[1] = og.ysize; G.no[2] = og.zsize;
-      const bool fits = og.xsize > 0 && og.ysize > 0 && og.zsize > 0 && og.xsize <= cap_o && og.ysize <= cap_o &&
-                        og.zsize <= cap_o;
-      if (sep && fits) {
-        G.valid = 1;
-        for (int k = 0; k < 3; ++k) { G.oorg[k] = og.origin[k]; G.sinv_d[k] = sinv[5 * k]; G.sinv_t[k] = sinv[12 + k]; }
-        G.od[0] = xd[0]; G.od[1] = yd[1]; G.od[2] = zd[2];
-        G.cc_xt = (og.xsize + 31) / 32;
-        G.cc_zc = (og.zsize + kZChunkFit - 1) / kZChunkFit;
-        G.cc_items = G.cc_xt * ((og.ysize + kRowsFit - 1) / kRowsFit) * G.cc_zc;
-      }
-    }
+    setup_target(G, sg, ok, T, cap_o);
     out[p] = G;
   }
   // exclusive prefixes (npose <= a few thousand: one thread, after everyone has written)
@@ -402,6 +408,61 @@ __global__ void __launch_bounds__(128) pose_tables_kernel(const PoseGeom *__rest
     else e = geom::axis_entry(ax, g, G.oorg[ax], G.od[ax], T.inv[5 * ax], T.inv[12 + ax], nsrcB[ax]);
     tab[((size_t)p * 6 + which) * cap_o + g] = e;
   }
+}
+
+// The density map of a rigidly TRANSLATED structure is the same array of voxels on a translated frame: QuickSurf's
+// grid hangs on the atoms' bounding box (origin = min - pad), so moving every atom by t moves the origin by t and
+// leaves every (atom - origin) difference -- hence every voxel -- unchanged up to the rounding of the additions.
+// pose_retarget_kernel re-aims the already splatted grids of a batch at the frame shifted by `shift` from where they
+// were splatted (org0, saved on the first call): new origin, new intersection with the target, new cc work items;
+// pose_tables_kernel and the cc kernel then score the translated candidates without a second splat.
+__global__ void __launch_bounds__(256) pose_retarget_kernel(PoseGeom *__restrict__ geo, float *__restrict__ org0, int npose, float sx,
+                                                            float sy, float sz, int save, float gs, int cap_o, TargetGeom T,
+                                                            int *__restrict__ totals) {
+  const float shift[3] = {sx, sy, sz};
+  for (int p = threadIdx.x; p < npose; p += blockDim.x) {
+    PoseGeom G = geo[p];
+    vt_grid sg;
+    const bool ok = G.tiles[0] > 0;
+    for (int k = 0; k < 3; ++k) {
+      if (save) org0[3 * p + k] = G.org[k];
+      G.org[k] = org0[3 * p + k] + shift[k];
+      sg.origin[k] = (double)G.org[k];
+      sg.xaxis[k] = sg.yaxis[k] = sg.zaxis[k] = 0.0;
+      const float ax = (float)(G.nv[k] - 1) * gs;
+      if (k == 0) sg.xaxis[0] = (double)ax;
+      if (k == 1) sg.yaxis[1] = (double)ax;
+      if (k == 2) sg.zaxis[2] = (double)ax;
+    }
+    sg.xsize = G.nv[0]; sg.ysize = G.nv[1]; sg.zsize = G.nv[2];
+    setup_target(G, sg, ok, T, cap_o);
+    geo[p] = G;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int i = 0; i < npose; ++i) { geo[i].cc_base = c; c += geo[i].cc_items; }
+    totals[1] = c;
+    totals[5] = 0;   // the cc kernel's task queue
+  }
+}
+
+int batch_retarget(const AtomSet &as, PoseBatch &pb, int npose, const float shift[3], bool first, const vt_grid *target) {
+  VT_REQUIRE_CTX();
+  Ctx &c = ctx();
+  if (!target || npose > pb.B || npose > 1024) { set_error("batch_retarget: bad arguments"); return 1; }
+  if (!pb.d_org0 && dev_alloc((void **)&pb.d_org0, sizeof(float) * 3 * (size_t)pb.B)) return 2;
+  TargetGeom T;
+  memset(&T, 0, sizeof(T));
+  T.grid = *target;
+  grid_inverse(*target, false, T.inv);
+  T.present = 1;
+  pose_retarget_kernel<<<1, 256, 0, c.stream>>>(pb.d_geom, pb.d_org0, npose, shift[0], shift[1], shift[2], first ? 1 : 0, as.prm.gs,
+                                                 pb.cap_o, T, pb.d_totals);
+  VT_LAUNCHED();
+  pose_tables_kernel<<<npose, 128, 0, c.stream>>>(pb.d_geom, T, pb.cap_o, pb.d_tab);
+  VT_LAUNCHED();
+  return 0;
 }
 
 int batch_prepare(const AtomSet &as, PoseBatch &pb, int npose, const PrepPose *d_prep, const float com[3],
