@@ -51,8 +51,9 @@ struct AtomSet {
   float4 *d_const = nullptr;  // per atom: arinv, radlim^2, radlim/gs, radius
   float4 *d_group = nullptr;  // per group: centre (origin frame) + bounding-sphere radius
   float *d_gcut = nullptr;    // per group: largest cutoff (gausslim * sigma) of its atoms
-  int *h_perm = nullptr;      // sorted position -> caller's atom index (host)
-  float *h_radii = nullptr;   // radii in the caller's order (host)
+  float *d_rawpos = nullptr;  // coordinates in the caller's order (the last upload)
+  float *d_rawrad = nullptr;  // radii in the caller's order
+  int *d_perm = nullptr;      // sorted position -> caller's atom index
   float maxrad = 0.f, pad = 0.f;
   float bound_center[3] = {0, 0, 0};
   float bound_radius = 0.f;   // all atoms within this distance of bound_center
