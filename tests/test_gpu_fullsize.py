@@ -220,3 +220,68 @@ def test_fit_rejects_skewed_target():
     T = vt.VolMap(g, np.random.default_rng(82).random(g.n, dtype=np.float32))
     with pytest.raises(vt.VoltoolGpuError):
         vt.FitContext(pos, radii, T, 5.0)
+
+
+# ------------------------------------------------------------------------------------------ round 2 kernels at size
+def test_blur_one_pass_tma_equals_two_kernel_form_large(monkeypatch):
+    """384 x 264 x 200 (ragged 16 x 64 tiles), sigma 0.6 / 1 / 2: the one-pass tensor-map TMA form (default up to
+    sigma 1) and the two-kernel form produce the same bits"""
+    nx, ny, nz = 384, 264, 200
+    g = vt.Grid.make((0, 0, 0), (nx, ny, nz), 1.0)
+    a = np.random.default_rng(401).random(g.n, dtype=np.float32)
+    A = vt.VolMap(g, a)
+    for sigma in (0.6, 1.0, 2.0):
+        monkeypatch.setenv("VOLTOOL_BLUR_MODE", "tma")
+        one = A.clone().gaussian_blur(sigma).data
+        monkeypatch.setenv("VOLTOOL_BLUR_MODE", "two")
+        two = A.clone().gaussian_blur(sigma).data
+        monkeypatch.delenv("VOLTOOL_BLUR_MODE")
+        dflt = A.clone().gaussian_blur(sigma).data
+        assert np.array_equal(bits(one), bits(two)) and np.array_equal(bits(dflt), bits(two)), sigma
+
+
+def test_lean_correlate_equals_ring_kernel_large(monkeypatch):
+    """320^3 x 320^3, B offset by half a voxel in x: the packed regular-sampling kernel (tensor-map TMA ring) and the
+    general ring kernel see the same samples -- identical voxel count, sums equal to the order of the float partials,
+    and identical bits for the two-map ops"""
+    n = 320
+    g, a = big_map(n, 402)
+    gb = vt.Grid.make((0.5, 0, 0), (n, n, n), 1.0)
+    b = np.random.default_rng(403).random(gb.n, dtype=np.float32)
+    A, B = vt.VolMap(g, a), vt.VolMap(gb, b)
+    for thr in (-FLT_MAX, 0.5):
+        cc1, n1, s1 = vt.cc_threaded(A, B, thr, full=True)
+        monkeypatch.setenv("VOLTOOL_CC_NOLEAN", "1")
+        cc0, n0, s0 = vt.cc_threaded(A, B, thr, full=True)
+        monkeypatch.delenv("VOLTOOL_CC_NOLEAN")
+        assert n1 == n0 and abs(cc1 - cc0) <= 1e-7
+        assert np.allclose(s1, s0, rtol=1e-6)
+    for op in (vt.add, vt.multiply):
+        o1 = op(A, B).data
+        monkeypatch.setenv("VOLTOOL_CC_NOLEAN", "1")
+        o0 = op(A, B).data
+        monkeypatch.delenv("VOLTOOL_CC_NOLEAN")
+        assert np.array_equal(bits(o1), bits(o0))
+
+
+def test_vol_com_bit_exact_on_a_noisy_padded_256_map():
+    """the cfg2-style target (density in the middle of a zero-padded 256^3 map + signed noise everywhere): the float
+    sums random-walk through the noise, which is the hard case for the parallel evaluation; bits must equal the
+    sequential loop's (numpy float32 cumulative arithmetic in voxel order)"""
+    n = 256
+    g = vt.Grid.make((0, 0, 0), (n, n, n), 1.0)
+    r = np.random.default_rng(404)
+    z, y, x = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    blob = np.exp(-((x - 130.0) ** 2 + (y - 120.0) ** 2 + (z - 125.0) ** 2) / (2 * 30.0 ** 2)).astype(np.float32)
+    d = (blob + np.float32(0.02) * r.standard_normal((n, n, n)).astype(np.float32)).astype(np.float32).reshape(-1)
+    com = vt.VolMap(g, d).vol_com()
+    # sequential float32 sums in voxel order: np.add.accumulate keeps float32 and adds left to right
+    want = np.empty(3, np.float32)
+    mass = np.float64(0.0)
+    for k, coord in enumerate((x, y, z)):
+        addend = (d * coord.reshape(-1).astype(np.float32)).astype(np.float32)
+        want[k] = np.add.accumulate(addend, dtype=np.float32)[-1]
+    mass = np.add.accumulate(d.astype(np.float64))[-1]
+    scale = np.float32(1.0 / mass)
+    want = (scale * want).astype(np.float32)
+    assert np.array_equal(bits(com), bits(want)), (com, want)

@@ -766,6 +766,7 @@ int k_blur(const float *src, float *dst, float *tmp, int nx, int ny, int nz, con
   // one pass over HBM with tensor-map TMA staging (vt_blur_tma.cu): the faster form for short kernels (R <= 3, i.e.
   // sigma <= 1 voxel; 512^3: 0.34 vs 0.41 ms at sigma 1, 0.29 vs 0.39 ms at sigma 0.6), where its per-plane
   // handshakes are not yet outweighed by the taps; longer kernels keep the two-kernel form unless asked ("tma")
+  // ("two": the two-kernel form whatever the radius, for comparisons)
   if ((bmode && !strcmp(bmode, "tma")) || (!bmode && R <= 3 && (long)nx * ny * nz >= (1L << 22))) {
     const int rc = k_blur_tma(src, dst, nx, ny, nz, w, R);
     if (rc == 0) { prof_end(PK_BLUR); return 0; }
