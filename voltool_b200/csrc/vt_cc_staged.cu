@@ -399,7 +399,16 @@ struct LeanMap {
   int y0, z0;        // source row of output row 0, source plane of output plane zlo
 };
 
-constexpr int kLeanWarps = 6;                           // consumer warps, one group of Y rows each (256 threads: 128 registers each at 2 CTAs / SM)
+// shape (measured at 512^3 / 1024^3, correlate with a half-voxel offset): 6 warps x 4 rows at 128 registers 0.396 / 2.84 ms;
+// 8 warps x 2 rows at 94 registers 0.355 / 2.71 ms (kept: more warps hide the ring and table latencies better than
+// longer rows amortise the x lerps); 10 warps x 2 rows at 80 registers (spills) 0.438 / 3.16 ms; six ring stages
+// instead of four: no change
+#ifndef LEAN_WARPS
+#define LEAN_WARPS 8
+#define LEAN_Y 2
+#define LEAN_CTAS 2
+#endif
+constexpr int kLeanWarps = LEAN_WARPS;                           // consumer warps, one group of LEAN_Y rows each
 constexpr int kLeanThreads = (kLeanWarps + 2) * 32;
 
 template <int Y> struct LeanShape {
@@ -446,7 +455,7 @@ __device__ __forceinline__ void lean_take(const float *__restrict__ ring, unsign
 }
 
 template <int Y, int MODE>
-__global__ void __launch_bounds__(kLeanThreads, 2)
+__global__ void __launch_bounds__(kLeanThreads, LEAN_CTAS)
     cc_lean_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, LeanMap A, LeanMap B,
                    const AxisEntry *__restrict__ tAx, const AxisEntry *__restrict__ tAy,
                    const AxisEntry *__restrict__ tAz, const AxisEntry *__restrict__ tBx, const AxisEntry *__restrict__ tBy,
@@ -754,7 +763,7 @@ static int launch_lean(const staged::LeanMap lm[2], int nx, int ny, int zlo, int
     return 1;   // no tensor maps: the caller takes the row-copy ring kernel
   const int zchunk = 64;
   const long work = (long)((nx + 63) / 64) * ((ny + TY - 1) / TY) * ((zhi - zlo + zchunk - 1) / zchunk);
-  const int grid = (int)std::min<long>(work, (long)c.sm_count * 2);
+  const int grid = (int)std::min<long>(work, (long)c.sm_count * LEAN_CTAS);
   prof_begin(MODE == 0 ? PK_CC : PK_BINARY);
   cc_lean_kernel<Y, MODE><<<grid, kLeanThreads, smem, c.stream>>>(tmA, tmB, lm[0], lm[1], d_tab + off[0], d_tab + off[1], d_tab + off[2],
                                                                   d_tab + off[3], d_tab + off[4], d_tab + off[5], nx, ny, zchunk,
@@ -774,8 +783,8 @@ static int launch_staged(const DevMap &A, const DevMap &B, int nx, int ny, int n
   if (zlo_out) { *zlo_out = zlo; *zhi_out = zhi; }
   {
     LeanMap lm[2];
-    if (!getenv("VOLTOOL_CC_NOLEAN") && lean_ok<Y>(host_tab, off, nx, ny, zlo, zhi, A, B, lm)) {
-      const int lrc = launch_lean<Y, MODE>(lm, nx, ny, zlo, zhi, off, d_tab, thr_f, partials, ticket, dout, ba);
+    if (!getenv("VOLTOOL_CC_NOLEAN") && lean_ok<LEAN_Y>(host_tab, off, nx, ny, zlo, zhi, A, B, lm)) {
+      const int lrc = launch_lean<LEAN_Y, MODE>(lm, nx, ny, zlo, zhi, off, d_tab, thr_f, partials, ticket, dout, ba);
       if (lrc != 1) return lrc;
     }
   }
