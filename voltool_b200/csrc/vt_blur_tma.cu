@@ -1,8 +1,8 @@
 // vt_blur_tma.cu -- VolumetricData::gaussian_blur (VolumetricData.C:977-997) in ONE pass over HBM.
 //
 // A CTA owns a TXW x TYH column of the map and marches along z.  Per source plane:
-//   (load)  one elected thread issues a 3-D tensor-map TMA box load (cp.async.bulk.tensor.3d, completion on an
-//           mbarrier) of the tile + its x/y halo, S planes ahead.  TMA zero-fills what lies outside the map; the
+//   (load)  one lane of a producer warp issues a 3-D tensor-map TMA box load (cp.async.bulk.tensor.3d, completion on
+//           an mbarrier) of the tile + its x/y halo, S planes ahead.  TMA zero-fills what lies outside the map; the
 //           tiles on the map border overwrite those cells with the clamp-to-edge value before the x pass.
 //   (x)     a thread per staged row: 16 + 2 RA floats by 16-byte shared loads, 16 outputs as 8 packed pairs.  A pair
 //           (j, j+1) receives input i as tap k of j and tap k-1 of j+1: FFMA2 with the input broadcast and the weight
@@ -203,11 +203,12 @@ __device__ __forceinline__ void mbar_arrive(unsigned int bar) {
 // column is staged by two tiles in x, the y halo rows by two in y) hit L2 while that plane is still resident.
 //
 // No block barrier in the steady state.  Planes flow through two shared-memory rings guarded by mbarriers:
-//   raw[S]  TMA boxes (full: the TMA's byte count; empty: the ROWS threads that x-passed the plane)
-//   T[D]    x-blurred planes, transposed (full: the ROWS x-pass threads; empty: all threads after their y window)
+//   raw[S]  TMA boxes, issued by a ninth (producer) warp S planes ahead
+//           (full: the TMA's byte count; empty: the warps that x-passed the plane)
+//   T[D]    x-blurred planes, transposed (full: the warps of the x pass; empty: every warp after its y window)
 // The x pass of THREE planes is spread over the whole CTA (thread t: row t % ROWS of plane 3g + t / ROWS), one
 // group of three planes ahead of the y / z work, so every thread carries the same load and warps only ever wait
-// for data, not for each other.
+// for data, not for each other.  What this costs and why it is the default only for short kernels: DESIGN.md 3.5.
 // warps that hold x-role rows of the planes q with q % 3 == k (threads k ROWS .. (k + 1) ROWS - 1)
 template <int ROWS>
 __host__ __device__ constexpr int x_warps(int k) { return ((k + 1) * ROWS - 1) / 32 - (k * ROWS) / 32 + 1; }
