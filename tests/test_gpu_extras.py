@@ -206,3 +206,26 @@ def test_search_grid_shared_splat_equals_per_pose_path(oracle, monkeypatch):
     assert i1 == i0 and np.array_equal(p1, p0) and abs(c1 - c0) <= 1e-5 * abs(c0)
     assert i1 // 27 == 0 and tuple(p1[3:]) == (0.0, 1.5, 0.0)              # the planted rotation and shift
     ctx.close()
+
+
+def test_new_entry_points_edge_cases(oracle):
+    """error behaviour and degenerate arguments of the round-2 entry points"""
+    gA, gB = OGrid.make((0, 0, 0), (8, 8, 8), 1.0), OGrid.make((100, 100, 100), (8, 8, 8), 1.0)
+    A, B = vt.VolMap(G(gA), rng_map(1, gA.n)), vt.VolMap(G(gB), rng_map(2, gB.n))
+    with pytest.raises(vt.VoltoolGpuError):
+        vt.cc_maps(A, B)                                   # the maps do not overlap
+    cc, best, tab = vt.density_rotate(A, vt.VolMap(G(gA), rng_map(3, gA.n)), 30, 0, (3.5, 3.5, 3.5), -1.0)
+    assert cc == -1.0 and best is None and tab.size == 0   # an empty loop leaves the running best alone
+    # tsteps = 0: the grid search is the arg max of the plain pose list, first maximum wins
+    pos, radii, mass = make_structure(400, 9.0, seed=91)
+    gT, t = make_target(oracle, pos, radii, 5.0, 1.0, rot=(24, 48, 0), noise=0.02, seed=92, mass=mass)
+    target = vt.VolMap(G(gT), t)
+    com = vt.measure_center(pos, mass)
+    ctx = vt.FitContext(pos, radii, target, 5.0)
+    rots = np.array([[0, 0, 0], [24, 48, 0], [24, 48, 0], [48, 24, 0]], np.float32)
+    bcc, bidx, bpose, allcc = ctx.search_grid(com, rots, 0, 0.0, want_all=True)
+    flat = ctx.eval_poses(com, vt.FitContext.make_poses(rots))
+    assert np.array_equal(bits(allcc), bits(flat)) and bidx == 1 and bcc == flat[1] and np.array_equal(bpose[:3], rots[1])
+    with pytest.raises(vt.VoltoolGpuError):
+        ctx.search_grid(com, np.zeros((0, 3), np.float32), 1, 1.0)
+    ctx.close()
