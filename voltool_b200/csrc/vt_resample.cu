@@ -300,11 +300,11 @@ __device__ __forceinline__ f32x2 cubic_half2(f32x2 y0, f32x2 y1, f32x2 y2, f32x2
 
 constexpr int kMLines = kSY + 3;
 constexpr int kMPairs = kMLines * kSX / 2;                       // x-sweep items are done two at a time
-constexpr int kMIt = (kMPairs + kThreads - 1) / kThreads;
 constexpr int kRawW = kSX + 3, kRawP = kSX + 4;                   // raw tile: columns tx0-1 .. tx0+kSX+1, row pitch
 constexpr int kRawN = kMLines * kRawW;                            // elements staged per plane
-constexpr int kRawIt = (kRawN + kThreads - 1) / kThreads;
 constexpr int kRawStages = 4;                                     // planes in flight: kRawStages - 1
+// RPT output rows per thread: 4 (256 threads, 3 CTAs per SM) or 2 (512 threads, 2 CTAs per SM: a third more warps)
+constexpr int kMarchRows = 2;
 
 __device__ __forceinline__ void cp_async4(float *smem_dst, const void *gsrc) {
   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
@@ -314,9 +314,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(kThreads, 3) supersample_march_kernel(const float *__restrict__ src, int ox, int oy,
-                                                                        int oz, float *__restrict__ dst, int nx, int ny,
-                                                                        int xt, int yt, int *__restrict__ tiny_flag) {
+template <int RPT>
+__global__ void __launch_bounds__(kSX * (kOY / RPT), RPT == 4 ? 3 : 2)
+    supersample_march_kernel(const float *__restrict__ src, int ox, int oy, int oz, float *__restrict__ dst, int nx, int ny, int xt,
+                             int yt, int *__restrict__ tiny_flag) {
+  constexpr int kThreads = kSX * (kOY / RPT);                        // (shadows the file-wide 256)
+  constexpr int kMIt = (kMPairs + kThreads - 1) / kThreads;
+  constexpr int kRawIt = (kRawN + kThreads - 1) / kThreads;
+  constexpr int NL = RPT / 2 + 3;                                    // x-lines a thread reads per plane
   __shared__ __align__(16) float lines[2][kMLines * kOX];
   __shared__ float raw[kRawStages][kMLines * kRawP];
   const int tid = threadIdx.x;
@@ -393,62 +398,64 @@ __global__ void __launch_bounds__(kThreads, 3) supersample_march_kernel(const fl
     }
   };
 
-  // ---- y / z sweeps: output columns X and X + 64, four output rows 4 rg ..
+  // ---- y / z sweeps: output columns X and X + 64, RPT output rows RPT rg ..
   const int X = tid & (kSX - 1), rg = tid >> 6;
-  unsigned int smask = 0;   // bit j: row j of column X is inside the map; bit 4 + j: column X + 64
+  unsigned int smask = 0;   // bit j: row j of column X is inside the map; bit RPT + j: column X + 64
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const bool rowok = Y0 + 4 * rg + j < ny;
+  for (int j = 0; j < RPT; ++j) {
+    const bool rowok = Y0 + RPT * rg + j < ny;
     if (rowok && X0 + X < nx) smask |= 1u << j;
-    if (rowok && X0 + X + kSX < nx) smask |= 16u << j;
+    if (rowok && X0 + X + kSX < nx) smask |= (1u << RPT) << j;
   }
   // this thread's four output rows in the even plane 2p of the current step (only dereferenced when
   // that plane exists); the odd plane written in the same step, 2(p-2)+1, lies 3 planes below
-  unsigned long long oe[4];
+  unsigned long long oe[RPT];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) oe[j] = (unsigned long long)(dst + (2L * (gbeg - 1) * nxy + (long)(Y0 + 4 * rg + j) * nx + X0 + X));
+  for (int j = 0; j < RPT; ++j) oe[j] = (unsigned long long)(dst + (2L * (gbeg - 1) * nxy + (long)(Y0 + RPT * rg + j) * nx + X0 + X));
   const unsigned long long ostep = 2ull * nxy * sizeof(float), oback = 3ull * nxy * sizeof(float);
-  f32x2 A[4], B[4], C[4], D[4];
+  f32x2 A[RPT], B[RPT], C[RPT], D[RPT];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) A[j] = B[j] = C[j] = D[j] = 0ull;
+  for (int j = 0; j < RPT; ++j) A[j] = B[j] = C[j] = D[j] = 0ull;
 
-  auto plane_step = [&](int s, const f32x2 (&w0)[4], const f32x2 (&w1)[4], const f32x2 (&w2)[4], f32x2 (&w3)[4]) {
+  auto plane_step = [&](int s, const f32x2 (&w0)[RPT], const f32x2 (&w1)[RPT], const f32x2 (&w2)[RPT], f32x2 (&w3)[RPT]) {
     const int p = gbeg - 1 + s;
     cp_async_wait<kRawStages - 3>();   // this thread's copies of plane s+1 have landed ...
     __syncthreads();      // ... and everybody's; lines[s&1] is complete; lines[(s+1)&1] and the oldest raw stage are free
     if (s + 1 < nsteps) x_sweep(s + 1);
     const float *ln = lines[s & 1];
-    f32x2 L[5];
+    f32x2 L[NL];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) L[k] = pack2(ln[(2 * rg + k) * kOX + X], ln[(2 * rg + k) * kOX + X + kSX]);
+    for (int k = 0; k < NL; ++k)
+      L[k] = pack2(ln[((RPT / 2) * rg + k) * kOX + X], ln[((RPT / 2) * rg + k) * kOX + X + kSX]);
     stage_plane();        // plane s + kRawStages - 1
-    w3[0] = L[1];                                               // even output rows: copies (:783-794)
-    w3[2] = L[2];
-    w3[1] = cubic_half2(L[0], L[1], L[2], L[3], c125, c25, c5);  // odd rows (:841-875)
-    w3[3] = cubic_half2(L[1], L[2], L[3], L[4], c125, c25, c5);
+#pragma unroll
+    for (int i = 0; i < RPT / 2; ++i) {
+      w3[2 * i] = L[i + 1];                                                         // even output rows: copies (:783-794)
+      w3[2 * i + 1] = cubic_half2(L[i], L[i + 1], L[i + 2], L[i + 3], c125, c25, c5);  // odd rows (:841-875)
+    }
     if (p >= gbeg && p < gend) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < RPT; ++j) {
         float a, b;
         unpack2(w3[j], a, b);
         float *o = reinterpret_cast<float *>(oe[j]);
         if ((smask >> j) & 1u) __stcs(o, a);
-        if ((smask >> (4 + j)) & 1u) __stcs(o + kSX, b);
+        if ((smask >> (RPT + j)) & 1u) __stcs(o + kSX, b);
       }
     }
     const int g = p - 2;   // odd plane 2g+1 from planes g-1, g, g+1, g+2 = p
     if (g >= gbeg && g < gend && g <= oz - 2) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < RPT; ++j) {
         float a, b;
         unpack2(cubic_half2(w0[j], w1[j], w2[j], w3[j], c125, c25, c5), a, b);
         float *o = reinterpret_cast<float *>(oe[j] - oback);
         if ((smask >> j) & 1u) __stcs(o, a);
-        if ((smask >> (4 + j)) & 1u) __stcs(o + kSX, b);
+        if ((smask >> (RPT + j)) & 1u) __stcs(o + kSX, b);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) oe[j] += ostep;
+    for (int j = 0; j < RPT; ++j) oe[j] += ostep;
   };
 #pragma unroll
   for (int k = 0; k < kRawStages - 1; ++k) stage_plane();
@@ -488,7 +495,7 @@ int k_supersample(const float *src, int ox, int oy, int oz, float *dst) {
         VT_CUDA(cudaMallocHost((void **)&h_flag, sizeof(int)));
       }
       VT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx().stream));
-      supersample_march_kernel<<<(unsigned int)work, kThreads, 0, ctx().stream>>>(src, ox, oy, oz, dst, nx, ny, xt, yt, d_flag);
+      supersample_march_kernel<kMarchRows><<<(unsigned int)work, kSX * (kOY / kMarchRows), 0, ctx().stream>>>(src, ox, oy, oz, dst, nx, ny, xt, yt, d_flag);
       VT_LAUNCHED();
       VT_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
       VT_CUDA(cudaStreamSynchronize(ctx().stream));
