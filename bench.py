@@ -421,7 +421,8 @@ def run_ours(args):
                 "frac": (achieved / fp32_peak) if achieved else None,
                 "traffic": splat_traffic(args, P * K / max(splat_n, 1))[0],
                 "traffic_source": splat_traffic(args, P * K / max(splat_n, 1))[1],
-                "peak_source": f"{props['sm_count']} SMs x 128 lanes x 2 x sm_max_mhz ({peaks['source']} MEASURED_PEAKS); "
+                "peak_source": f"{props['sm_count']} SMs x 128 lanes x 2 x sm_max_mhz ({peaks['source']} MEASURED_PEAKS); measured on this "
+                               "pool: 127.9 FMA/clk/SM with FFMA2 chains (profiles/r2_fp32_peak_microbench.txt); "
                                "no tensor cores: nothing here is a contraction",
                 "binding_resource": "shared-memory pipe, then instruction issue (ncu of this kernel inside the fit step: l1tex 74 % "
                                     "busy, issue 72 %; profiles/r2l_splat_list_kernel_summary.txt); only ~1 in 7 (atom, voxel) "
